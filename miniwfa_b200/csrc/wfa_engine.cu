@@ -1,0 +1,1069 @@
+/*
+ * wfa_engine.cu -- sm_100a engine for the exact dual-affine wavefront alignment hot path.
+ *
+ * What runs here (reference: /root/reference/miniwfa.c @ 66770a3):
+ *   step kernel   = wf_next_score / wf_next_tb (:261-308) fused with the extend loop and
+ *                   wf_extend1_padded (:400-411, :212-226), the edge rule (:325-326), the
+ *                   termination test (:405-409), wf_stripe_shrink (:144-171) and the stop
+ *                   tests (:421-425); in low-memory pass 1 also wf_next_seg's replay (:503-523)
+ *                   and wf_snapshot1 (:451-474);
+ *   after the loop: wf_traceback_seg (:528-549) and wf_traceback (:329-377), on the device.
+ *
+ * Two kernel families share the same templated step:
+ *   wfa_cta_kernel  : persistent, one CTA per pair taken from a work queue; the per-score
+ *                     barrier is __syncthreads().  Used for batches.
+ *   wfa_grid_kernel : cooperative launch, every SM works on the same pair; the per-score
+ *                     barrier is a grid barrier.  Used for a few large pairs.
+ *
+ * Data layout in HBM (per slot = per resident CTA in cta mode, one slot in grid mode):
+ *   ring  : int32 [nring][5][pitch], nring = max_pen+1 score slices x {H,E1,F1,E2,F2};
+ *           cell of diagonal d lives at index d + doff; every slice is written together
+ *           with nring cells of NEG_INF on both sides (same invariant as miniwfa.c:96-99),
+ *           so the +-1 neighbour reads never need a range test.
+ *   arena : traceback bytes, one row per score (bump-allocated, 1 byte per cell exactly as
+ *           miniwfa.c:42) -- or, during low-memory pass 1, the snapshots.
+ *   rowtab: int64 per score: arena offset of that score's row minus its first index.
+ * Sequences: each padded to a 16-byte boundary with >=16 zero bytes of slack; match runs
+ * are clamped to the matrix, so no sentinel characters are required.
+ *
+ * No CPU fallback exists: every entry point aborts if no CUDA device is usable.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include <atomic>
+#include "mwf_b200.h"
+#include "kalloc.h"
+
+#define NEG_INF (-0x40000000) /* WF_NEG_INF, miniwfa.c:67 */
+
+enum { MODE_SCORE = 0, MODE_TB = 1, MODE_SEG1 = 2 };
+enum { ST_OK = 0, ST_STOPPED = 1, ST_ARENA = 2, ST_SHRINK = 3, ST_CORRUPT = 4 };
+enum { FL_LO = 1, FL_HI = 2, FL_DONE = 4, FL_LAST_SHIFT = 4 };
+
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	fprintf(stderr, "[mwf_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+	abort(); } } while (0)
+
+struct Pen { int x, oe1, e1, oe2, e2, nring; };
+
+struct PairDesc {
+	long long t_off, q_off; /* byte offsets into the sequence buffer (16-byte aligned) */
+	int tl, ql;
+	long long cigar_off;    /* word offset of this pair's CIGAR buffer */
+	int cigar_cap, pad_;
+};
+
+struct PairOut {
+	int s, n_cigar;
+	long long n_iter;
+	long long cigar_pos;    /* word offset of the first CIGAR word */
+	int status, pad_;
+};
+
+struct KParams {
+	Pen pen;
+	int is_tb, step, max_s;
+	long long max_iter;
+	int n_pairs, single_pair;
+	const int *order;
+	unsigned int *queue;
+	const PairDesc *pairs;
+	PairOut *outs;
+	const uint8_t *seq;
+	uint32_t *cigar;
+	int pitch;
+	int32_t *ring, *ring2;
+	long long ring_stride;      /* int32 per slot */
+	uint8_t *arena;
+	long long arena_stride;     /* bytes per slot */
+	long long *rowtab;
+	long long rowtab_stride;    /* entries per slot */
+	int *snaphdr;
+	long long *snapoff;
+	int *seg;
+	int snap_cap;
+	unsigned int *bar;          /* grid barrier: {count, generation} */
+	int *gflags;                /* grid mode flag words [3] */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* small device helpers                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ int4 ld_ring4(const int32_t *p) { return __ldcg(reinterpret_cast<const int4*>(p)); }
+__device__ __forceinline__ int  ld_ring1(const int32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ void st_ring4(int32_t *p, int4 v) { __stcg(reinterpret_cast<int4*>(p), v); }
+__device__ __forceinline__ void st_ring1(int32_t *p, int v) { __stcg(p, v); }
+
+/* 4 bytes starting at byte position pos (little endian), from a 4-byte aligned word array */
+__device__ __forceinline__ uint32_t seq_word(const uint32_t *__restrict__ w, int pos)
+{
+	const int i = pos >> 2;
+	return __funnelshift_r(__ldg(w + i), __ldg(w + i + 1), (pos & 3) << 3);
+}
+
+/* longest common prefix of ts[k+1..] and qs[d+k+1..], clamped so that k <= kmax = min(tl-1, ql-1-d).
+ * Same value as wf_extend1_padded (miniwfa.c:212-226), whose sentinels stop at the same place. */
+__device__ __forceinline__ int extend_run(const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q, int k, int d, int kmax)
+{
+	int tp = k + 1, qp = d + k + 1;
+	while (k < kmax) {
+		const uint32_t x = seq_word(T, tp) ^ seq_word(Q, qp);
+		if (x) { k += (__ffs(x) - 1) >> 3; break; }
+		k += 4, tp += 4, qp += 4;
+	}
+	return min(k, kmax);
+}
+
+__device__ __forceinline__ bool on_matrix(int d, int k, int tl, int ql) /* good_diag, miniwfa.c:139-142 */
+{
+	return k >= -1 && k < tl && d + k >= -1 && d + k < ql;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* thread groups: the set of threads that cooperates on one pair                               */
+/* ------------------------------------------------------------------------------------------ */
+
+struct CtaGroup {
+	int *fl; /* shared memory flag words [3] */
+	__device__ __forceinline__ int rank() const { return threadIdx.x; }
+	__device__ __forceinline__ int size() const { return blockDim.x; }
+	__device__ __forceinline__ bool leader_cta() const { return true; }
+	__device__ __forceinline__ void sync() { __syncthreads(); }
+	__device__ __forceinline__ void flag_or(int k, int v) { atomicOr(&fl[k], v); }
+	__device__ __forceinline__ int flag_get(int k) const { return ((volatile int*)fl)[k]; }
+	__device__ __forceinline__ void flag_zero(int k) { if (threadIdx.x == 0) fl[k] = 0; }
+};
+
+struct GridGroup {
+	int *fl;            /* global flag words [3] */
+	unsigned int *bar;  /* {count, generation} */
+	unsigned int gen;   /* generation this CTA waits to leave */
+	__device__ __forceinline__ int rank() const { return blockIdx.x * blockDim.x + threadIdx.x; }
+	__device__ __forceinline__ int size() const { return gridDim.x * blockDim.x; }
+	__device__ __forceinline__ bool leader_cta() const { return blockIdx.x == 0; }
+	__device__ __forceinline__ void sync()
+	{
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			__threadfence();
+			const unsigned int arrived = atomicAdd(&bar[0], 1u);
+			if (arrived == gridDim.x - 1) {
+				bar[0] = 0;
+				__threadfence();
+				atomicAdd(&bar[1], 1u);
+			} else {
+				while (*((volatile unsigned int*)&bar[1]) == gen) { }
+			}
+			__threadfence();
+		}
+		++gen;
+		__syncthreads();
+	}
+	__device__ __forceinline__ void flag_or(int k, int v) { atomicOr(&fl[k], v); }
+	__device__ __forceinline__ int flag_get(int k) const { return __ldcg(&fl[k]); }
+	__device__ __forceinline__ void flag_zero(int k) { if (blockIdx.x == 0 && threadIdx.x == 0) __stcg(&fl[k], 0); }
+};
+
+/* everything one pair needs, resolved for the slot it runs in */
+struct Job {
+	int tl, ql, doff;
+	const uint32_t *T, *Q;
+	const uint8_t *T8, *Q8;
+	int32_t *ring, *ring2;
+	uint8_t *arena;
+	long long arena_cap;
+	long long *rowtab;
+	long long rowtab_cap;
+	int *snaphdr;
+	long long *snapoff;
+	int *seg;
+	int *slo, *shi; /* shared: [lo,hi] of every ring slice */
+	int *scr;       /* shared scratch, >= 4 ints */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* wf_stripe_shrink (miniwfa.c:144-171)                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ bool diag_alive(const Job &J, const Pen &pen, int pitch, int d)
+{
+	for (int j = 0; j < pen.nring; ++j) {
+		if (d < J.slo[j] || d > J.shi[j]) continue;
+		const int32_t *p = J.ring + (size_t)j * 5 * pitch + d + J.doff;
+		for (int a = 0; a < 5; ++a)
+			if (on_matrix(d, ld_ring1(p + (size_t)a * pitch), J.tl, J.ql)) return true;
+	}
+	return false;
+}
+
+/* every CTA of the group runs this redundantly and gets the same answer */
+__device__ bool shrink_band(const Job &J, const Pen &pen, int pitch, int &wflo, int &wfhi)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (warp == 0) {
+		int nl = wfhi + 1;
+		for (int base = wflo; base <= wfhi; base += 32) {
+			const int d = base + lane;
+			const unsigned m = __ballot_sync(0xffffffffu, d <= wfhi && diag_alive(J, pen, pitch, d));
+			if (m) { nl = base + __ffs(m) - 1; break; }
+		}
+		if (lane == 0) J.scr[0] = nl;
+	}
+	__syncthreads();
+	const int nl = J.scr[0];
+	if (warp == 0) {
+		int nh = nl - 1;
+		for (int base = wfhi; base >= nl; base -= 32) {
+			const int d = base - lane;
+			const unsigned m = __ballot_sync(0xffffffffu, d >= nl && diag_alive(J, pen, pitch, d));
+			if (m) { nh = base - (__ffs(m) - 1); break; }
+		}
+		if (lane == 0) J.scr[1] = nh;
+	}
+	__syncthreads();
+	const int nh = J.scr[1];
+	__syncthreads(); /* scr is reused */
+	if (nl > wfhi || nh < nl) return false; /* the reference asserts here (:157, :169) */
+	wflo = nl, wfhi = nh;
+	return true;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* one score step over the band [lo,hi]                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+struct StepRows {
+	const int32_t *Hx, *Ho1, *Ho2, *pE1, *pF1, *pE2, *pF2; /* wf_next_prep, miniwfa.c:252-257 */
+	int32_t *nH, *nE1, *nF1, *nE2, *nF2;
+};
+
+__device__ __forceinline__ StepRows step_rows(int32_t *ring, const Pen &pen, int pitch, int nslot)
+{
+	StepRows r;
+	const int n = pen.nring;
+	int sx = nslot - pen.x, so1 = nslot - pen.oe1, so2 = nslot - pen.oe2, se1 = nslot - pen.e1, se2 = nslot - pen.e2;
+	if (sx < 0) sx += n;
+	if (so1 < 0) so1 += n;
+	if (so2 < 0) so2 += n;
+	if (se1 < 0) se1 += n;
+	if (se2 < 0) se2 += n;
+	const size_t p = (size_t)pitch;
+	r.Hx  = ring + (size_t)sx  * 5 * p;
+	r.Ho1 = ring + (size_t)so1 * 5 * p;
+	r.Ho2 = ring + (size_t)so2 * 5 * p;
+	r.pE1 = ring + ((size_t)se1 * 5 + 1) * p;
+	r.pF1 = ring + ((size_t)se1 * 5 + 2) * p;
+	r.pE2 = ring + ((size_t)se2 * 5 + 3) * p;
+	r.pF2 = ring + ((size_t)se2 * 5 + 4) * p;
+	r.nH  = ring + (size_t)nslot * 5 * p;
+	r.nE1 = r.nH + p, r.nF1 = r.nH + 2 * p, r.nE2 = r.nH + 3 * p, r.nF2 = r.nH + 4 * p;
+	return r;
+}
+
+#define I4(v, j) ((j) == 0 ? (v).x : (j) == 1 ? (v).y : (j) == 2 ? (v).z : (v).w)
+
+/*
+ * Each thread owns 4 consecutive diagonals (one aligned int4 of every row); the d-1 / d+1
+ * neighbours inside the int4 come from registers, across threads from warp shuffles, and
+ * across warps from two scalar loads.  Returns this thread's flag bits.
+ */
+template<int MODE, class G>
+__device__ __forceinline__ int step_cells(G &g, const Job &J, const StepRows &R, const StepRows &S,
+                                          int lo, int hi, uint8_t *tbrow)
+{
+	const int lane = threadIdx.x & 31;
+	const int doff = J.doff, tl = J.tl, ql = J.ql;
+	const int ilo = lo + doff, ihi = hi + doff, i0 = ilo & ~3;
+	const int dfin = ql - tl;
+	int myfl = 0;
+	for (int wbase = i0 + 4 * (g.rank() - lane); wbase <= ihi; wbase += 4 * g.size()) {
+		const int idx = wbase + 4 * lane;
+		const bool act = idx <= ihi + 1;
+		int4 ho1, pe1, pf1, ho2, pe2, pf2, hx;
+		if (act) {
+			ho1 = ld_ring4(R.Ho1 + idx); pe1 = ld_ring4(R.pE1 + idx); pf1 = ld_ring4(R.pF1 + idx);
+			ho2 = ld_ring4(R.Ho2 + idx); pe2 = ld_ring4(R.pE2 + idx); pf2 = ld_ring4(R.pF2 + idx);
+			hx  = ld_ring4(R.Hx + idx);
+		} else {
+			ho1 = pe1 = pf1 = ho2 = pe2 = pf2 = hx = make_int4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
+		}
+		int4 sho1, spe1, spf1, sho2, spe2, spf2, shx; /* provenance labels (low-memory pass 1) */
+		if (MODE == MODE_SEG1) {
+			if (act) {
+				sho1 = ld_ring4(S.Ho1 + idx); spe1 = ld_ring4(S.pE1 + idx); spf1 = ld_ring4(S.pF1 + idx);
+				sho2 = ld_ring4(S.Ho2 + idx); spe2 = ld_ring4(S.pE2 + idx); spf2 = ld_ring4(S.pF2 + idx);
+				shx  = ld_ring4(S.Hx + idx);
+			} else {
+				sho1 = spe1 = spf1 = sho2 = spe2 = spf2 = shx = make_int4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
+			}
+		}
+		/* what this cell offers to its right neighbour (insertion, d+1) and left neighbour (deletion, d-1) */
+		int A1[6], A2[6], C1[6], C2[6];       /* index j+1 for element j; [0] = from the left, [5] = from the right */
+		int bA1[6], bA2[6], bC1[6], bC2[6];   /* 1 iff the extend source strictly beats the open source */
+		int LA1[6], LA2[6], LC1[6], LC2[6];   /* offered labels */
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int o1 = I4(ho1, j), o2 = I4(ho2, j);
+			const int e1 = I4(pe1, j), e2 = I4(pe2, j), f1 = I4(pf1, j), f2 = I4(pf2, j);
+			A1[j + 1] = max(o1, e1), A2[j + 1] = max(o2, e2);
+			C1[j + 1] = max(o1, f1) + 1, C2[j + 1] = max(o2, f2) + 1;
+			if (MODE != MODE_SCORE) {
+				bA1[j + 1] = o1 < e1, bA2[j + 1] = o2 < e2, bC1[j + 1] = o1 < f1, bC2[j + 1] = o2 < f2;
+			}
+			if (MODE == MODE_SEG1) {
+				LA1[j + 1] = bA1[j + 1] ? I4(spe1, j) : I4(sho1, j);
+				LA2[j + 1] = bA2[j + 1] ? I4(spe2, j) : I4(sho2, j);
+				LC1[j + 1] = bC1[j + 1] ? I4(spf1, j) : I4(sho1, j);
+				LC2[j + 1] = bC2[j + 1] ? I4(spf2, j) : I4(sho2, j);
+			}
+		}
+		A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
+		A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
+		C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+		C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+		if (MODE != MODE_SCORE) {
+			const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+			const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
+			bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+		}
+		if (MODE == MODE_SEG1) {
+			LA1[0] = __shfl_up_sync(0xffffffffu, LA1[4], 1);
+			LA2[0] = __shfl_up_sync(0xffffffffu, LA2[4], 1);
+			LC1[5] = __shfl_down_sync(0xffffffffu, LC1[1], 1);
+			LC2[5] = __shfl_down_sync(0xffffffffu, LC2[1], 1);
+		}
+		if (lane == 0 && act) { /* left neighbour belongs to another warp */
+			const int o1 = ld_ring1(R.Ho1 + idx - 1), e1 = ld_ring1(R.pE1 + idx - 1);
+			const int o2 = ld_ring1(R.Ho2 + idx - 1), e2 = ld_ring1(R.pE2 + idx - 1);
+			A1[0] = max(o1, e1), A2[0] = max(o2, e2);
+			if (MODE != MODE_SCORE) bA1[0] = o1 < e1, bA2[0] = o2 < e2;
+			if (MODE == MODE_SEG1) {
+				LA1[0] = bA1[0] ? ld_ring1(S.pE1 + idx - 1) : ld_ring1(S.Ho1 + idx - 1);
+				LA2[0] = bA2[0] ? ld_ring1(S.pE2 + idx - 1) : ld_ring1(S.Ho2 + idx - 1);
+			}
+		}
+		if (lane == 31 && act) { /* right neighbour belongs to another warp */
+			const int o1 = ld_ring1(R.Ho1 + idx + 4), f1 = ld_ring1(R.pF1 + idx + 4);
+			const int o2 = ld_ring1(R.Ho2 + idx + 4), f2 = ld_ring1(R.pF2 + idx + 4);
+			C1[5] = max(o1, f1) + 1, C2[5] = max(o2, f2) + 1;
+			if (MODE != MODE_SCORE) bC1[5] = o1 < f1, bC2[5] = o2 < f2;
+			if (MODE == MODE_SEG1) {
+				LC1[5] = bC1[5] ? ld_ring1(S.pF1 + idx + 4) : ld_ring1(S.Ho1 + idx + 4);
+				LC2[5] = bC2[5] ? ld_ring1(S.pF2 + idx + 4) : ld_ring1(S.Ho2 + idx + 4);
+			}
+		}
+		if (!act) continue; /* after the shuffles: inactive lanes have nothing to store */
+
+		int vH[4], vE1[4], vF1[4], vE2[4], vF2[4], st[4], kmax[4];
+		int lH[4], lE1[4], lF1[4], lE2[4], lF2[4];
+		uint32_t tbw = 0;
+		bool ext[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2], F2 = C2[j + 2];
+			const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = I4(hx, j) + 1;
+			const int H = max(hxp, gmx);
+			vE1[j] = E1, vE2[j] = E2, vF1[j] = F1, vF2[j] = F2, vH[j] = H;
+			if (MODE != MODE_SCORE) { /* the 7-bit pack, miniwfa.c:290-306 */
+				const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4));
+				st[j] = z;
+				tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j);
+				if (MODE == MODE_SEG1) { /* replay, miniwfa.c:506-522 */
+					lE1[j] = LA1[j], lE2[j] = LA2[j], lF1[j] = LC1[j + 2], lF2[j] = LC2[j + 2];
+					lH[j] = z == 0 ? I4(shx, j) : z == 1 ? lE1[j] : z == 2 ? lF1[j] : z == 3 ? lE2[j] : lF2[j];
+				}
+			}
+			const int ii = idx + j, d = ii - doff;
+			const bool in = ii >= ilo && ii <= ihi;
+			if (in && (H >= -1 || E1 >= -1 || F1 >= -1 || E2 >= -1 || F2 >= -1)) { /* edge rule, :325-326 */
+				if (d == lo) myfl |= FL_LO;
+				if (d == hi) myfl |= FL_HI;
+			}
+			kmax[j] = min(tl - 1, ql - 1 - d);
+			ext[j] = in && H >= -1 && d + H >= -1 && H <= kmax[j]; /* :402 */
+		}
+		/* first probe of the match run for all four cells (loads issued together) */
+		uint32_t px[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int d = idx + j - doff;
+			const int tp = ext[j] ? vH[j] + 1 : 0, qp = ext[j] ? d + vH[j] + 1 : 0;
+			px[j] = seq_word(J.T, tp) ^ seq_word(J.Q, qp);
+		}
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			if (!ext[j]) continue;
+			const int d = idx + j - doff, h0 = vH[j];
+			int k;
+			if (px[j]) k = min(h0 + ((__ffs(px[j]) - 1) >> 3), kmax[j]);
+			else k = extend_run(J.T, J.Q, min(h0 + 4, kmax[j]), d, kmax[j]);
+			if (d == dfin && k == tl - 1) { /* reached the end of both sequences, :405-409 */
+				myfl |= FL_DONE;
+				if (MODE == MODE_TB && k == h0) myfl |= st[j] << FL_LAST_SHIFT;
+			}
+			vH[j] = k;
+		}
+		/* stores */
+		if (idx >= ilo && idx + 3 <= ihi) {
+			st_ring4(R.nH + idx, make_int4(vH[0], vH[1], vH[2], vH[3]));
+			st_ring4(R.nE1 + idx, make_int4(vE1[0], vE1[1], vE1[2], vE1[3]));
+			st_ring4(R.nF1 + idx, make_int4(vF1[0], vF1[1], vF1[2], vF1[3]));
+			st_ring4(R.nE2 + idx, make_int4(vE2[0], vE2[1], vE2[2], vE2[3]));
+			st_ring4(R.nF2 + idx, make_int4(vF2[0], vF2[1], vF2[2], vF2[3]));
+			if (MODE == MODE_SEG1) {
+				st_ring4(S.nH + idx, make_int4(lH[0], lH[1], lH[2], lH[3]));
+				st_ring4(S.nE1 + idx, make_int4(lE1[0], lE1[1], lE1[2], lE1[3]));
+				st_ring4(S.nF1 + idx, make_int4(lF1[0], lF1[1], lF1[2], lF1[3]));
+				st_ring4(S.nE2 + idx, make_int4(lE2[0], lE2[1], lE2[2], lE2[3]));
+				st_ring4(S.nF2 + idx, make_int4(lF2[0], lF2[1], lF2[2], lF2[3]));
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const int ii = idx + j;
+				if (ii < ilo || ii > ihi) continue;
+				st_ring1(R.nH + ii, vH[j]); st_ring1(R.nE1 + ii, vE1[j]); st_ring1(R.nF1 + ii, vF1[j]);
+				st_ring1(R.nE2 + ii, vE2[j]); st_ring1(R.nF2 + ii, vF2[j]);
+				if (MODE == MODE_SEG1) {
+					st_ring1(S.nH + ii, lH[j]); st_ring1(S.nE1 + ii, lE1[j]); st_ring1(S.nF1 + ii, lF1[j]);
+					st_ring1(S.nE2 + ii, lE2[j]); st_ring1(S.nF2 + ii, lF2[j]);
+				}
+			}
+		}
+		if (MODE == MODE_TB && idx <= ihi) __stcs(reinterpret_cast<uint32_t*>(tbrow + idx), tbw);
+	}
+	return myfl;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* wf_snapshot1 (miniwfa.c:451-474): copy the provenance ring out, relabel every cell          */
+/* ------------------------------------------------------------------------------------------ */
+
+template<class G>
+__device__ bool take_snapshot(G &g, const Job &J, const Pen &pen, int pitch, int cur, int s,
+                              int snap_idx, int snap_cap, long long &used)
+{
+	const int n = pen.nring, hw = 2 + 2 * n;
+	long long total = 0;
+	for (int j = 0; j < n; ++j) {
+		int slot = cur + 1 + j; if (slot >= n) slot -= n;
+		total += 5LL * (J.shi[slot] - J.slo[slot] + 1);
+	}
+	if (snap_idx >= snap_cap || used + total * 4 > J.arena_cap || total > 0x7fffffffLL) return false;
+	int32_t *x = reinterpret_cast<int32_t*>(J.arena + used);
+	int *hdr = J.snaphdr + (size_t)snap_idx * hw;
+	if (g.rank() == 0) { hdr[0] = s; hdr[1] = (int)total; J.snapoff[snap_idx] = used; }
+	int pref = 0;
+	for (int j = 0; j < n; ++j) { /* oldest slice first */
+		int slot = cur + 1 + j; if (slot >= n) slot -= n;
+		const int slo = J.slo[slot], cnt = 5 * (J.shi[slot] - slo + 1);
+		if (g.rank() == 0) { hdr[2 + 2 * j] = slo; hdr[3 + 2 * j] = cnt; }
+		int32_t *base = J.ring2 + (size_t)slot * 5 * pitch + J.doff;
+		for (int u = g.rank(); u < cnt; u += g.size()) {
+			const int d = slo + u / 5, a = u % 5;
+			int32_t *p = base + (size_t)a * pitch + d;
+			x[pref + u] = ld_ring1(p);
+			st_ring1(p, pref + u);
+		}
+		pref += cnt;
+	}
+	used += (total * 4 + 15) & ~15LL;
+	return true;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* the score loop of mwf_wfa_core (:397-426) / mwf_wfa_seg (:569-589)                           */
+/* ------------------------------------------------------------------------------------------ */
+
+struct PassOut {
+	int s, last, n_snap;
+	long long n_iter;
+};
+
+template<int MODE, class G>
+__device__ int run_pass(G &g, const KParams &P, const Job &J, int n_seg, PassOut &out)
+{
+	const Pen pen = P.pen;
+	const int n = pen.nring, m1 = n, pitch = P.pitch;
+	const int tl = J.tl, ql = J.ql, doff = J.doff;
+	/* wf_stripe_init (:103-121): every slice is [0,0] holding NEG_INF (pads included) */
+	for (int t = g.rank(); t < n * 5 * (2 * m1 + 1); t += g.size()) {
+		const int row = t / (2 * m1 + 1), c = t % (2 * m1 + 1);
+		st_ring1(J.ring + (size_t)row * pitch + doff - m1 + c, NEG_INF);
+		if (MODE == MODE_SEG1) st_ring1(J.ring2 + (size_t)row * pitch + doff - m1 + c, NEG_INF);
+	}
+	for (int t = threadIdx.x; t < n; t += blockDim.x) J.slo[t] = J.shi[t] = 0;
+	g.flag_zero(0); g.flag_zero(1); g.flag_zero(2);
+	g.sync();
+	if (g.rank() == 0) { /* score 0: H[0] = -1, then its match run */
+		const int kmax = min(tl - 1, ql - 1);
+		const int k = extend_run(J.T, J.Q, -1, 0, kmax);
+		st_ring1(J.ring + doff, k);
+		if (MODE == MODE_SEG1) st_ring1(J.ring2 + doff, -1);
+		if (k == tl - 1 && k == ql - 1) g.flag_or(0, FL_DONE);
+	}
+	g.sync();
+	int s = 0, cur = 0, wflo = 0, wfhi = 0, sid = 0, n_snap = 0;
+	long long n_iter = 0, used = 0;
+	out.s = 0, out.last = MODE == MODE_SEG1 ? -1 : 0, out.n_snap = 0, out.n_iter = 0;
+	if (g.flag_get(0) & FL_DONE) return ST_OK;
+
+	for (;;) {
+		if (MODE == MODE_TB && sid < n_seg && J.seg[2 * sid] == s) { /* band collapse, :413-416 */
+			wflo = wfhi = J.seg[2 * sid + 1];
+			++sid;
+		}
+		const int lo = wflo > -tl ? wflo - 1 : -tl, hi = wfhi < ql ? wfhi + 1 : ql; /* :417-418 */
+		const int snew = s + 1, nslot = cur + 1 == n ? 0 : cur + 1;
+		if (MODE == MODE_SEG1 && snew % P.step == 0) { /* :585-586 */
+			if (!take_snapshot(g, J, pen, pitch, cur, s, n_snap, P.snap_cap, used)) return ST_ARENA;
+			++n_snap;
+			g.sync();
+		}
+		uint8_t *tbrow = 0;
+		if (MODE == MODE_TB) { /* wf_tb_add (:33-44): one byte per cell of this score */
+			const int i0 = (lo + doff) & ~3;
+			const long long rowsize = ((hi + doff - i0) | 3) + 1;
+			if (used + rowsize > J.arena_cap || snew >= J.rowtab_cap) return ST_ARENA;
+			tbrow = J.arena + used - i0;
+			if (g.rank() == 0) J.rowtab[snew] = used - i0;
+			used += rowsize;
+		}
+		const StepRows R = step_rows(J.ring, pen, pitch, nslot);
+		StepRows S = R;
+		if (MODE == MODE_SEG1) S = step_rows(J.ring2, pen, pitch, nslot);
+		const int myfl = step_cells<MODE>(g, J, R, S, lo, hi, tbrow);
+		for (int t = g.rank(); t < 2 * m1 * 5; t += g.size()) { /* NEG_INF pads, :96-99 */
+			const int a = t / (2 * m1), c = t % (2 * m1);
+			const int idx = c < m1 ? lo + doff - 1 - c : hi + doff + 1 + (c - m1);
+			st_ring1(R.nH + (size_t)a * pitch + idx, NEG_INF);
+			if (MODE == MODE_SEG1) st_ring1(S.nH + (size_t)a * pitch + idx, NEG_INF);
+		}
+		if (threadIdx.x == 0) J.slo[nslot] = lo, J.shi[nslot] = hi;
+		g.flag_zero((snew + 1) % 3);
+		if (myfl) g.flag_or(snew % 3, myfl);
+		g.sync();
+		const int fl = g.flag_get(snew % 3);
+		s = snew, cur = nslot;
+		n_iter += hi - lo + 1; /* :421 */
+		if (fl & FL_LO) wflo = lo;
+		if (fl & FL_HI) wfhi = hi;
+		if ((s & 0xff) == 0) { /* :420 */
+			if (!shrink_band(J, pen, pitch, wflo, wfhi)) return ST_SHRINK;
+			g.sync(); /* the oldest slice is overwritten next step; everyone must be done reading it */
+		}
+		out.s = s, out.n_iter = n_iter, out.n_snap = n_snap;
+		if (MODE != MODE_SEG1 && ((P.max_iter > 0 && n_iter > P.max_iter) || (P.max_s > 0 && s > P.max_s)))
+			return ST_STOPPED; /* :422-425; tested before the next extend, so it wins over FL_DONE */
+		if (fl & FL_DONE) {
+			if (MODE == MODE_TB) out.last = fl >> FL_LAST_SHIFT;
+			if (MODE == MODE_SEG1) out.last = ld_ring1(J.ring2 + (size_t)cur * 5 * pitch + (ql - tl) + doff); /* :577 */
+			return ST_OK;
+		}
+	}
+}
+
+/* wf_traceback_seg (miniwfa.c:528-549); one thread */
+__device__ bool trace_checkpoints(const Job &J, const Pen &pen, int n_snap, int last)
+{
+	const int n = pen.nring, hw = 2 + 2 * n;
+	for (int j = n_snap - 1; j >= 0; --j) {
+		const int *hdr = J.snaphdr + (size_t)j * hw;
+		const int32_t *x = reinterpret_cast<const int32_t*>(J.arena + J.snapoff[j]);
+		int k, m = 0;
+		for (k = 0; k < n; ++k) {
+			if (last >= m && last < m + hdr[3 + 2 * k]) break;
+			m += hdr[3 + 2 * k];
+		}
+		if (k == n) return false;
+		J.seg[2 * j] = hdr[0] - (n - k - 1);
+		J.seg[2 * j + 1] = hdr[2 + 2 * k] + (last - m) / 5;
+		last = __ldcg(x + last);
+	}
+	return last == -1;
+}
+
+/* wf_traceback (miniwfa.c:329-377); one warp, all lanes walk in lock step, match runs 32 bytes at a time.
+ * CIGAR words are written backwards from cig_end so that no final reversal is needed. */
+__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end)
+{
+	const int lane = threadIdx.x & 31, doff = J.doff;
+	int i = J.ql - 1, k = J.tl - 1, row = s_final, n_out = 0, cur_op = -1;
+	uint32_t cur_len = 0;
+	uint32_t *wp = cig_end;
+#define CIG_PUSH(op_, len_) do { \
+		if ((op_) == cur_op) cur_len += (len_); \
+		else { if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; } cur_op = (op_), cur_len = (len_); } \
+	} while (0)
+	while (i >= 0 && k >= 0) {
+		if (last == 0) { /* greedy backward matches, :335-341 */
+			int run = 0;
+			for (;;) {
+				const int ii = i - lane, kk = k - lane;
+				const bool same = ii >= 0 && kk >= 0 && J.Q8[ii] == J.T8[kk];
+				const unsigned m = __ballot_sync(0xffffffffu, !same);
+				if (m) { const int c = __ffs(m) - 1; run += c, i -= c, k -= c; break; }
+				run += 32, i -= 32, k -= 32;
+			}
+			if (run > 0) CIG_PUSH(7, (uint32_t)run);
+			if (i < 0 || k < 0) break;
+		}
+		const int x = __ldcg(J.arena + J.rowtab[row] + (i - k + doff));
+		const int state = last == 0 ? (x & 7) : last;
+		const int ext = state > 0 ? (x >> (state + 2)) & 1 : 0;
+		if (state == 0) { CIG_PUSH(8, 1u); --i, --k; row -= pen.x; }
+		else if (state == 1) { CIG_PUSH(1, 1u); --i; row -= ext ? pen.e1 : pen.oe1; }
+		else if (state == 3) { CIG_PUSH(1, 1u); --i; row -= ext ? pen.e2 : pen.oe2; }
+		else if (state == 2) { CIG_PUSH(2, 1u); --k; row -= ext ? pen.e1 : pen.oe1; }
+		else { CIG_PUSH(2, 1u); --k; row -= ext ? pen.e2 : pen.oe2; }
+		last = (state > 0 && ext) ? state : 0;
+	}
+	if (i >= 0) CIG_PUSH(1, (uint32_t)(i + 1));       /* :368 */
+	else if (k >= 0) CIG_PUSH(2, (uint32_t)(k + 1));  /* :369 */
+	if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; }
+#undef CIG_PUSH
+	return n_out;
+}
+
+/* mwf_wfa_exact (:603-615) for one pair in one slot */
+template<class G>
+__device__ void run_pair(G &g, const KParams &P, int pi, int slot, int *smem)
+{
+	const PairDesc pd = P.pairs[pi];
+	Job J;
+	const int n = P.pen.nring;
+	J.tl = pd.tl, J.ql = pd.ql;
+	J.doff = pd.tl + n + 8;
+	J.T8 = P.seq + pd.t_off, J.Q8 = P.seq + pd.q_off;
+	J.T = reinterpret_cast<const uint32_t*>(J.T8), J.Q = reinterpret_cast<const uint32_t*>(J.Q8);
+	J.ring = P.ring + (size_t)slot * P.ring_stride;
+	J.ring2 = P.ring2 ? P.ring2 + (size_t)slot * P.ring_stride : 0;
+	J.arena = P.arena ? P.arena + (size_t)slot * P.arena_stride : 0;
+	J.arena_cap = P.arena_stride;
+	J.rowtab = P.rowtab ? P.rowtab + (size_t)slot * P.rowtab_stride : 0;
+	J.rowtab_cap = P.rowtab_stride;
+	J.snaphdr = P.snaphdr ? P.snaphdr + (size_t)slot * P.snap_cap * (2 + 2 * n) : 0;
+	J.snapoff = P.snapoff ? P.snapoff + (size_t)slot * P.snap_cap : 0;
+	J.seg = P.seg ? P.seg + (size_t)slot * P.snap_cap * 2 : 0;
+	J.scr = smem + 4;
+	J.slo = smem + 8, J.shi = smem + 8 + n;
+
+	PassOut po;
+	int st, n_cigar = 0, n_seg = 0;
+	if (!P.is_tb) {
+		st = run_pass<MODE_SCORE>(g, P, J, 0, po);
+	} else {
+		st = ST_OK;
+		if (P.step > 0) { /* low-memory mode: pass 1 finds the checkpoints (:610-611) */
+			st = run_pass<MODE_SEG1>(g, P, J, 0, po);
+			if (st == ST_OK) {
+				if (g.rank() == 0 && !trace_checkpoints(J, P.pen, po.n_snap, po.last)) g.flag_or(0, 1 << 30);
+				g.sync();
+				if (g.flag_get(0) & (1 << 30)) st = ST_CORRUPT;
+				n_seg = po.n_snap;
+				g.sync();
+			}
+		}
+		if (st == ST_OK) st = run_pass<MODE_TB>(g, P, J, n_seg, po);
+		if (st == ST_OK && g.leader_cta() && threadIdx.x < 32)
+			n_cigar = traceback_warp(J, P.pen, po.s, po.last, P.cigar + pd.cigar_off + pd.cigar_cap);
+	}
+	if (g.rank() == 0) {
+		PairOut o;
+		o.s = st == ST_OK ? po.s : -1;
+		o.n_cigar = n_cigar;
+		o.n_iter = po.n_iter;
+		o.cigar_pos = pd.cigar_off + pd.cigar_cap - n_cigar;
+		o.status = st, o.pad_ = 0;
+		P.outs[pi] = o;
+	}
+}
+
+__global__ void __launch_bounds__(512, 1) wfa_cta_kernel(const KParams P)
+{
+	extern __shared__ int smem[]; /* [0..2] flags, [3] queue slot, [4..7] scratch, then slo[n], shi[n] */
+	CtaGroup g;
+	g.fl = smem;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) smem[3] = (int)atomicAdd(P.queue, 1u);
+		__syncthreads();
+		const int qi = smem[3];
+		if (qi >= P.n_pairs) break;
+		run_pair(g, P, P.order[qi], blockIdx.x, smem);
+	}
+}
+
+__global__ void __launch_bounds__(512, 1) wfa_grid_kernel(const KParams P)
+{
+	extern __shared__ int smem[];
+	GridGroup g;
+	g.fl = P.gflags, g.bar = P.bar;
+	g.gen = *((volatile unsigned int*)&P.bar[1]);
+	run_pair(g, P, P.single_pair, 0, smem);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* host side                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+
+static std::atomic<int> g_device(-1), g_kernel(-1), g_threads(0);
+
+static int env_int(const char *name, int dflt)
+{
+	const char *v = getenv(name);
+	return v && *v ? atoi(v) : dflt;
+}
+
+extern "C" int mwf_b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" void mwf_b200_set_device(int dev) { g_device = dev; }
+
+extern "C" int mwf_b200_get_device(void)
+{
+	int d = g_device;
+	if (d < 0) {
+		d = env_int("MWF_B200_DEVICE", -1);
+		if (d < 0) d = env_int("LOCAL_RANK", 0);
+		const int n = mwf_b200_device_count();
+		if (n > 0) d %= n;
+		g_device = d;
+	}
+	return d;
+}
+
+extern "C" void mwf_b200_set_kernel(int kernel) { g_kernel = kernel; }
+extern "C" void mwf_b200_set_block_threads(int threads) { g_threads = threads; }
+
+static int pick_kernel_pref(void)
+{
+	int k = g_kernel;
+	if (k < 0) {
+		const char *v = getenv("MWF_B200_KERNEL");
+		k = MWF_B200_KERNEL_AUTO;
+		if (v && !strcmp(v, "cta")) k = MWF_B200_KERNEL_CTA;
+		else if (v && !strcmp(v, "grid")) k = MWF_B200_KERNEL_GRID;
+	}
+	return k;
+}
+
+struct mwf_b200_batch {
+	int dev, kernel, n, n_sm, threads, n_slots;
+	mwf_opt_t opt;
+	Pen pen;
+	bool is_tb;
+	cudaStream_t stream;
+	bool own_stream;
+	std::vector<int> tl, ql, order;
+	std::vector<PairDesc> pairs;
+	size_t seq_bytes, cigar_words;
+	uint8_t *d_seq, *h_seq;
+	PairDesc *d_pairs;
+	PairOut *d_outs, *h_outs;
+	int *d_order;
+	unsigned int *d_ctl; /* [0] queue, [1..2] grid barrier, [4..6] grid flags */
+	uint32_t *d_cigar;
+	int pitch;
+	long long ring_stride, arena_total, rowtab_stride;
+	int snap_cap;
+	int32_t *d_ring, *d_ring2;
+	uint8_t *d_arena;
+	long long *d_rowtab, *d_snapoff;
+	int *d_snaphdr, *d_seg;
+	cudaEvent_t ev0, ev1;
+	double kernel_ms;
+	int64_t launches, h2d, d2h;
+	bool ran;
+};
+
+static void die(const char *msg)
+{
+	fprintf(stderr, "[mwf_b200] %s\n", msg);
+	abort();
+}
+
+static long long gap_cost(const mwf_opt_t *o, long long len)
+{
+	if (len <= 0) return 0;
+	const long long a = o->o1 + len * (long long)o->e1, b = o->o2 + len * (long long)o->e2;
+	return a < b ? a : b;
+}
+
+extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t n_pairs, const int32_t *tl, const int32_t *ql)
+{
+	if (mwf_b200_device_count() <= 0) die("no CUDA device: this library has no CPU fallback");
+	if (opt->x <= 0 || opt->e1 <= 0 || opt->e2 <= 0 || opt->o1 < 0 || opt->o2 < 0)
+		die("penalties must satisfy x>0, e1>0, e2>0, o1>=0, o2>=0");
+	mwf_b200_batch_t *b = new mwf_b200_batch_t();
+	b->dev = mwf_b200_get_device();
+	CUDA_OK(cudaSetDevice(b->dev));
+	cudaDeviceProp prop;
+	CUDA_OK(cudaGetDeviceProperties(&prop, b->dev));
+	b->n_sm = prop.multiProcessorCount;
+	b->opt = *opt;
+	b->n = n_pairs;
+	b->is_tb = !!(opt->flag & MWF_F_CIGAR);
+	const bool seg = b->is_tb && opt->step > 0;
+	int max_pen = opt->x;
+	max_pen = std::max(max_pen, opt->o1 + opt->e1);
+	max_pen = std::max(max_pen, opt->o2 + opt->e2);
+	b->pen.x = opt->x, b->pen.oe1 = opt->o1 + opt->e1, b->pen.e1 = opt->e1;
+	b->pen.oe2 = opt->o2 + opt->e2, b->pen.e2 = opt->e2, b->pen.nring = max_pen + 1;
+	b->tl.assign(tl, tl + n_pairs);
+	b->ql.assign(ql, ql + n_pairs);
+	b->threads = g_threads > 0 ? (int)g_threads : env_int("MWF_B200_THREADS", 512);
+	if (b->threads < 64 || b->threads > 512 || b->threads % 32) die("block threads must be a multiple of 32 in [64,512]");
+
+	/* layout of sequences, CIGAR buffers, work order */
+	long long max_len = 0, max_sbound = 0;
+	size_t off = 0, cw = 0;
+	b->pairs.resize(n_pairs);
+	b->order.resize(n_pairs);
+	for (int i = 0; i < n_pairs; ++i) {
+		if (tl[i] < 0 || ql[i] < 0) die("negative sequence length");
+		PairDesc &p = b->pairs[i];
+		p.tl = tl[i], p.ql = ql[i];
+		p.t_off = (long long)off; off += ((size_t)tl[i] + 16 + 15) & ~(size_t)15;
+		p.q_off = (long long)off; off += ((size_t)ql[i] + 16 + 15) & ~(size_t)15;
+		p.cigar_off = (long long)cw, p.cigar_cap = b->is_tb ? tl[i] + ql[i] + 2 : 0, p.pad_ = 0;
+		cw += (size_t)p.cigar_cap;
+		max_len = std::max(max_len, (long long)tl[i] + ql[i]);
+		long long sb = gap_cost(opt, tl[i]) + gap_cost(opt, ql[i]);
+		if (opt->max_s > 0) sb = std::min(sb, (long long)opt->max_s + 1);
+		max_sbound = std::max(max_sbound, sb);
+		b->order[i] = i;
+	}
+	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
+		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
+	b->seq_bytes = off + 16, b->cigar_words = cw;
+
+	/* kernel family */
+	int pref = pick_kernel_pref();
+	if (pref == MWF_B200_KERNEL_AUTO)
+		pref = (n_pairs >= b->n_sm / 4 || max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
+	b->kernel = pref;
+	b->n_slots = pref == MWF_B200_KERNEL_GRID ? 1 : std::max(1, std::min(n_pairs, b->n_sm));
+
+	CUDA_OK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+	b->own_stream = true;
+	CUDA_OK(cudaEventCreate(&b->ev0));
+	CUDA_OK(cudaEventCreate(&b->ev1));
+
+	/* device workspaces */
+	const int n = b->pen.nring;
+	b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
+	b->ring_stride = (long long)n * 5 * b->pitch;
+	CUDA_OK(cudaMalloc(&b->d_seq, b->seq_bytes));
+	CUDA_OK(cudaMallocHost(&b->h_seq, b->seq_bytes));
+	memset(b->h_seq, 0, b->seq_bytes);
+	CUDA_OK(cudaMalloc(&b->d_pairs, sizeof(PairDesc) * std::max(1, n_pairs)));
+	CUDA_OK(cudaMalloc(&b->d_outs, sizeof(PairOut) * std::max(1, n_pairs)));
+	CUDA_OK(cudaMallocHost(&b->h_outs, sizeof(PairOut) * std::max(1, n_pairs)));
+	CUDA_OK(cudaMalloc(&b->d_order, sizeof(int) * std::max(1, n_pairs)));
+	CUDA_OK(cudaMalloc(&b->d_ctl, 64));
+	CUDA_OK(cudaMalloc(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots));
+	b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
+	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0;
+	if (b->is_tb) {
+		CUDA_OK(cudaMalloc(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw)));
+		b->rowtab_stride = max_sbound + 2;
+		CUDA_OK(cudaMalloc(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots));
+		if (seg) {
+			CUDA_OK(cudaMalloc(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots));
+			b->snap_cap = (int)(max_sbound / opt->step + 2);
+			CUDA_OK(cudaMalloc(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots));
+			CUDA_OK(cudaMalloc(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots));
+			CUDA_OK(cudaMalloc(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots));
+		}
+		/* traceback / snapshot arena: the worst case when it is small, else most of what is free */
+		size_t free_b = 0, total_b = 0;
+		CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+		const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
+		long long worst = (max_sbound + 2) * (max_len + 16);
+		if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
+		worst = (worst + 255) & ~255LL;
+		long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
+		if (per_slot < 4096) die("not enough free device memory for the traceback arena");
+		b->arena_total = per_slot * b->n_slots;
+		CUDA_OK(cudaMalloc(&b->d_arena, (size_t)b->arena_total));
+	}
+	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false;
+	return b;
+}
+
+extern "C" void mwf_b200_batch_set_stream(mwf_b200_batch_t *b, void *cuda_stream)
+{
+	if (b->own_stream) { CUDA_OK(cudaStreamDestroy(b->stream)); b->own_stream = false; }
+	b->stream = (cudaStream_t)cuda_stream;
+}
+
+extern "C" void mwf_b200_batch_upload(mwf_b200_batch_t *b, const char *const *ts, const char *const *qs)
+{
+	CUDA_OK(cudaSetDevice(b->dev));
+	for (int i = 0; i < b->n; ++i) {
+		const PairDesc &p = b->pairs[i];
+		if (p.tl) memcpy(b->h_seq + p.t_off, ts[i], (size_t)p.tl);
+		if (p.ql) memcpy(b->h_seq + p.q_off, qs[i], (size_t)p.ql);
+	}
+	CUDA_OK(cudaMemcpyAsync(b->d_seq, b->h_seq, b->seq_bytes, cudaMemcpyHostToDevice, b->stream));
+	CUDA_OK(cudaMemcpyAsync(b->d_pairs, b->pairs.data(), sizeof(PairDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
+	CUDA_OK(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int) * b->n, cudaMemcpyHostToDevice, b->stream));
+	b->h2d = (int64_t)b->seq_bytes + (int64_t)(sizeof(PairDesc) + sizeof(int)) * b->n;
+}
+
+static KParams make_params(const mwf_b200_batch_t *b, int n_slots)
+{
+	KParams P;
+	memset(&P, 0, sizeof(P));
+	P.pen = b->pen;
+	P.is_tb = b->is_tb, P.step = b->is_tb ? b->opt.step : 0, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter;
+	P.n_pairs = b->n, P.single_pair = 0;
+	P.order = b->d_order, P.queue = b->d_ctl;
+	P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.cigar = b->d_cigar;
+	P.pitch = b->pitch;
+	P.ring = b->d_ring, P.ring2 = b->d_ring2, P.ring_stride = b->ring_stride;
+	P.arena = b->d_arena, P.arena_stride = b->d_arena ? (b->arena_total / n_slots) & ~255LL : 0;
+	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
+	P.snaphdr = b->d_snaphdr, P.snapoff = b->d_snapoff, P.seg = b->d_seg, P.snap_cap = b->snap_cap;
+	P.bar = b->d_ctl + 1, P.gflags = (int*)(b->d_ctl + 4);
+	return P;
+}
+
+static void launch_cta(mwf_b200_batch_t *b, const KParams &P, int grid)
+{
+	const size_t smem = sizeof(int) * (8 + 2 * (size_t)b->pen.nring);
+	CUDA_OK(cudaMemsetAsync(b->d_ctl, 0, 64, b->stream));
+	wfa_cta_kernel<<<grid, b->threads, smem, b->stream>>>(P);
+	CUDA_OK(cudaGetLastError());
+	++b->launches;
+}
+
+static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
+{
+	const size_t smem = sizeof(int) * (8 + 2 * (size_t)b->pen.nring);
+	int per_sm = 0;
+	CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfa_grid_kernel, b->threads, smem));
+	if (per_sm < 1) die("grid kernel does not fit on an SM");
+	const int grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_GRID_CTAS_PER_SM", 1));
+	P.single_pair = pair;
+	CUDA_OK(cudaMemsetAsync(b->d_ctl, 0, 64, b->stream));
+	void *args[] = { (void*)&P };
+	CUDA_OK(cudaLaunchCooperativeKernel((void*)wfa_grid_kernel, dim3(grid), dim3(b->threads), args, smem, b->stream));
+	++b->launches;
+}
+
+extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
+{
+	CUDA_OK(cudaSetDevice(b->dev));
+	b->launches = 0;
+	CUDA_OK(cudaEventRecord(b->ev0, b->stream));
+	if (b->n > 0) {
+		if (b->kernel == MWF_B200_KERNEL_CTA) {
+			launch_cta(b, make_params(b, b->n_slots), b->n_slots);
+		} else {
+			const KParams P = make_params(b, 1);
+			for (int i = 0; i < b->n; ++i) launch_grid(b, P, b->order[i]);
+		}
+	}
+	CUDA_OK(cudaEventRecord(b->ev1, b->stream));
+	CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
+	b->ran = true;
+}
+
+extern "C" void mwf_b200_batch_wait(mwf_b200_batch_t *b)
+{
+	CUDA_OK(cudaSetDevice(b->dev));
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+	if (!b->ran) return;
+	float ms = 0;
+	CUDA_OK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+	b->kernel_ms = ms;
+	/* pairs whose slot ran out of arena are retried one at a time with the whole arena */
+	std::vector<int> retry;
+	for (int i = 0; i < b->n; ++i) {
+		const int st = b->h_outs[i].status;
+		if (st == ST_ARENA && b->kernel == MWF_B200_KERNEL_CTA && b->n_slots > 1) retry.push_back(i);
+		else if (st == ST_ARENA) die("device workspace exhausted (traceback/snapshot arena); use opt.step>0 or a smaller batch");
+		else if (st == ST_SHRINK) die("internal error: empty band after shrink");
+		else if (st == ST_CORRUPT) die("internal error: checkpoint chain is corrupt");
+	}
+	if (!retry.empty()) {
+		CUDA_OK(cudaEventRecord(b->ev0, b->stream));
+		KParams P = make_params(b, 1);
+		std::vector<int> one(1);
+		for (size_t r = 0; r < retry.size(); ++r) {
+			one[0] = retry[r];
+			CUDA_OK(cudaMemcpyAsync(b->d_order, one.data(), sizeof(int), cudaMemcpyHostToDevice, b->stream));
+			P.n_pairs = 1;
+			launch_cta(b, P, 1);
+			CUDA_OK(cudaStreamSynchronize(b->stream));
+		}
+		CUDA_OK(cudaEventRecord(b->ev1, b->stream));
+		CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int) * b->n, cudaMemcpyHostToDevice, b->stream));
+		CUDA_OK(cudaStreamSynchronize(b->stream));
+		CUDA_OK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+		b->kernel_ms += ms;
+		for (size_t r = 0; r < retry.size(); ++r)
+			if (b->h_outs[retry[r]].status == ST_ARENA)
+				die("device workspace exhausted (traceback/snapshot arena); use opt.step>0");
+	}
+}
+
+extern "C" void mwf_b200_batch_fetch(mwf_b200_batch_t *b, void *km, mwf_rst_t *r)
+{
+	mwf_b200_batch_wait(b);
+	b->d2h = (int64_t)sizeof(PairOut) * b->n;
+	for (int i = 0; i < b->n; ++i) {
+		const PairOut &o = b->h_outs[i];
+		r[i].s = o.s, r[i].n_iter = o.n_iter, r[i].n_cigar = 0, r[i].cigar = 0;
+		if (o.s >= 0 && o.n_cigar > 0) {
+			r[i].n_cigar = o.n_cigar;
+			r[i].cigar = (uint32_t*)kmalloc(km, sizeof(uint32_t) * (size_t)o.n_cigar);
+			CUDA_OK(cudaMemcpyAsync(r[i].cigar, b->d_cigar + o.cigar_pos, sizeof(uint32_t) * (size_t)o.n_cigar,
+			                        cudaMemcpyDeviceToHost, b->stream));
+			b->d2h += (int64_t)sizeof(uint32_t) * o.n_cigar;
+		}
+	}
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+}
+
+extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
+{
+	if (!b) return;
+	CUDA_OK(cudaSetDevice(b->dev));
+	cudaFree(b->d_seq); cudaFreeHost(b->h_seq); cudaFree(b->d_pairs); cudaFree(b->d_outs); cudaFreeHost(b->h_outs);
+	cudaFree(b->d_order); cudaFree(b->d_ctl); cudaFree(b->d_ring); cudaFree(b->d_ring2); cudaFree(b->d_arena);
+	cudaFree(b->d_rowtab); cudaFree(b->d_snapoff); cudaFree(b->d_snaphdr); cudaFree(b->d_seg); cudaFree(b->d_cigar);
+	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
+	if (b->own_stream) cudaStreamDestroy(b->stream);
+	delete b;
+}
+
+extern "C" double mwf_b200_batch_kernel_ms(const mwf_b200_batch_t *b) { return b->kernel_ms; }
+extern "C" int64_t mwf_b200_batch_launches(const mwf_b200_batch_t *b) { return b->launches; }
+extern "C" int mwf_b200_batch_kernel_used(const mwf_b200_batch_t *b) { return b->kernel; }
+extern "C" int64_t mwf_b200_batch_h2d_bytes(const mwf_b200_batch_t *b) { return b->h2d; }
+extern "C" int64_t mwf_b200_batch_d2h_bytes(const mwf_b200_batch_t *b) { return b->d2h; }
+
+extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pairs,
+                                    const int32_t *tl, const char *const *ts,
+                                    const int32_t *ql, const char *const *qs, mwf_rst_t *r)
+{
+	mwf_b200_batch_t *b = mwf_b200_batch_create(opt, n_pairs, tl, ql);
+	mwf_b200_batch_upload(b, ts, qs);
+	mwf_b200_batch_run(b);
+	mwf_b200_batch_fetch(b, km, r);
+	mwf_b200_batch_destroy(b);
+}

@@ -1,0 +1,35 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    """The built product library (compiles it if needed; nvcc cross-compiles without a GPU)."""
+    from miniwfa_b200 import build
+    build.build()
+    from miniwfa_b200 import api
+    return api.lib()
+
+
+def case_inputs(case):
+    from miniwfa_b200 import synth
+    if "synth" in case:
+        return synth.make_pair(*case["synth"])
+    return case["t"].encode("latin-1"), case["q"].encode("latin-1")

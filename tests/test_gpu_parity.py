@@ -1,0 +1,209 @@
+"""GPU: the CUDA path, called through the C-ABI (mwf_wfa_exact / mwf_wfa_exact_batch / mwf_b200_batch_*),
+against the reference's golden vectors, the oracle (and oracle/_ref when it travelled with the snapshot) on
+seeded random inputs, and size-independent properties at full size.  Bit-exact: s, n_iter, n_cigar, CIGAR words."""
+import random
+
+import pytest
+
+from conftest import case_inputs
+import miniwfa_b200 as mw
+from miniwfa_b200 import synth
+from miniwfa_b200.api import cigar_string
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [("cta", mw.KERNEL_CTA), ("grid", mw.KERNEL_GRID)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu(product_lib):
+    assert mw.device_count() > 0, "no CUDA device visible: the product has no CPU fallback"
+    yield
+    mw.set_kernel(mw.KERNEL_AUTO)
+
+
+def exact_cases(golden, big=False):
+    out = []
+    for c in golden:
+        if c.get("fn", "mwf_wfa_exact") != "mwf_wfa_exact":
+            continue
+        if c["name"].startswith(("n100k", "n20k")) != big:
+            continue
+        out.append(c)
+    return out
+
+
+def expect(c):
+    e = c["expect"]
+    return (e["s"], e["n_cigar"], e["n_iter"], e["cigar"])
+
+
+def got(r):
+    return (r[0], r[1], r[2], cigar_string(r[3]))
+
+
+@pytest.mark.parametrize("kname,kernel", KERNELS)
+def test_golden_single_pair_api(golden, kname, kernel):
+    """mwf_wfa_exact(), one call per golden case, with each kernel family."""
+    mw.set_kernel(kernel)
+    n = 0
+    for c in exact_cases(golden):
+        t, q = case_inputs(c)
+        if len(t) + len(q) == 0 and c["opt"].get("flag", 0) & 1:
+            continue  # the reference itself is undefined here (reads tb.a[-1])
+        r = mw.wfa_exact(mw.opt_init(**c["opt"]), t, q)
+        assert got(r) == expect(c), (kname, c["name"])
+        n += 1
+    assert n > 250
+
+
+def test_golden_batched(golden):
+    """The same golden cases submitted as batches (one batch per option set) through mwf_wfa_exact_batch."""
+    mw.set_kernel(mw.KERNEL_AUTO)
+    groups = {}
+    for c in exact_cases(golden):
+        t, q = case_inputs(c)
+        if len(t) + len(q) == 0 and c["opt"].get("flag", 0) & 1:
+            continue
+        groups.setdefault(tuple(sorted(c["opt"].items())), []).append((c, t, q))
+    assert len(groups) > 20
+    for key, items in groups.items():
+        rs = mw.wfa_exact_batch(mw.opt_init(**dict(key)), [(t, q) for _, t, q in items])
+        for (c, _, _), r in zip(items, rs):
+            assert got(r) == expect(c), c["name"]
+
+
+def test_empty_pair_with_cigar_is_defined():
+    r = mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR), b"", b"")
+    assert r == (0, 0, 0, [])
+    assert mw.wfa_exact_batch(mw.opt_init(), []) == []
+
+
+@pytest.mark.parametrize("kname,kernel", KERNELS)
+def test_golden_large(golden, kname, kernel):
+    mw.set_kernel(kernel)
+    for c in exact_cases(golden, big=True):
+        if kname == "cta" and c["name"].startswith("n100k"):
+            continue
+        t, q = case_inputs(c)
+        r = mw.wfa_exact(mw.opt_init(**c["opt"]), t, q)
+        assert got(r) == expect(c), (kname, c["name"])
+
+
+def mutate(rng, t, p):
+    q = bytearray()
+    for ch in t:
+        u = rng.random()
+        if u < p * 0.8:
+            q.append(rng.choice(b"ACGT"))
+        elif u < p * 0.9:
+            q.extend(bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 30))))
+            q.append(ch)
+        elif u < p:
+            pass
+        else:
+            q.append(ch)
+    return bytes(q)
+
+
+def random_opt(rng):
+    kw = {}
+    pre = rng.choice(["d", "d", "a", "e", "r", "r"])
+    if pre == "a":
+        kw.update(o2=4, e2=2)
+    elif pre == "e":
+        kw.update(x=1, o1=0, o2=0, e1=1, e2=1)
+    elif pre == "r":
+        kw.update(x=rng.randint(1, 9), o1=rng.randint(0, 8), e1=rng.randint(1, 4), o2=rng.randint(0, 30), e2=rng.randint(1, 3))
+    mode = rng.choice(["s", "c", "c", "p", "p", "stop"])
+    if mode != "s":
+        kw["flag"] = mw.F_CIGAR
+    if mode == "p":
+        kw["step"] = rng.choice([1, 2, 5, 7, 37, 500, 5000])
+    if mode == "stop":
+        kw[rng.choice(["max_s", "max_iter"])] = rng.randint(1, 20000)
+    return kw
+
+
+@pytest.mark.parametrize("kname,kernel", KERNELS)
+def test_random_differential(kname, kernel):
+    """Seeded random pairs and random valid penalty sets against the CPU checker."""
+    mw.set_kernel(kernel)
+    rng = random.Random(42 if kname == "cta" else 43)
+    for it in range(160):
+        n = rng.choice([0, 1, 2, 5, 17, 60, 200, 300, 1000, 3000]) if it % 20 else 9000
+        t = bytes(rng.choice(b"ACGT") for _ in range(n))
+        if rng.random() < 0.85:
+            q = mutate(rng, t, rng.choice([0, 0.01, 0.05, 0.15, 0.4]))
+        else:
+            q = bytes(rng.choice(b"ACGT") for _ in range(rng.randint(0, 400)))
+        kw = random_opt(rng)
+        if kw.get("step") == 1 and len(t) > 400:
+            kw["step"] = 3
+        if len(t) + len(q) == 0 and kw.get("flag"):
+            continue
+        want = orc.checker_exact(orc.make_opt(**kw), t, q)
+        assert mw.wfa_exact(mw.opt_init(**kw), t, q) == want, (kname, it, n, kw)
+
+
+def test_random_batch_ragged():
+    """One ragged batch (lengths 0..5000, including empty and unrelated pairs) per mode."""
+    mw.set_kernel(mw.KERNEL_AUTO)
+    rng = random.Random(99)
+    pairs = []
+    for i in range(200):
+        n = rng.choice([0, 1, 10, 100, 500, 2000, 5000])
+        t = bytes(rng.choice(b"ACGT") for _ in range(n))
+        q = mutate(rng, t, rng.choice([0, 0.02, 0.1, 0.3])) if i % 7 else bytes(rng.choice(b"ACGT") for _ in range(rng.randint(1, 300)))
+        if len(t) + len(q):
+            pairs.append((t, q))
+    for kw in ({}, {"flag": mw.F_CIGAR}, {"flag": mw.F_CIGAR, "step": 50}, {"flag": mw.F_CIGAR, "max_s": 300},
+               {"x": 1, "o1": 0, "o2": 0, "e1": 1, "e2": 1, "flag": mw.F_CIGAR}):
+        o = orc.make_opt(**kw)
+        want = [orc.checker_exact(o, t, q) for t, q in pairs]
+        assert mw.wfa_exact_batch(mw.opt_init(**kw), pairs) == want, kw
+
+
+def test_bytes_and_case_sensitivity():
+    mw.set_kernel(mw.KERNEL_AUTO)
+    o = mw.opt_init(flag=mw.F_CIGAR)
+    assert got(mw.wfa_exact(o, b"ACGTNNNNACGT", b"acgtNNNNacgt"))[:2] == (32, 3)
+    # all 256 byte values in use: the reference aborts (no free sentinel); the engine does not need sentinels
+    t = bytes(range(256)) * 2
+    q = t[:100] + b"\x00" + t[100:300] + t[305:]
+    r = mw.wfa_exact(o, t, q)
+    want = orc.oracle_exact(orc.make_opt(flag=1), t, q)
+    assert r == want and mw.cigar2score(o, r[3]) == (r[0], len(t), len(q))
+
+
+def test_full_size_properties():
+    """100 kb / 5 % (the BASELINE config-3 pair shape): score vs golden, CIGAR re-scoring, low-memory == high-memory."""
+    mw.set_kernel(mw.KERNEL_AUTO)
+    t, q = synth.make_pair(100000, 0.05, 0)
+    s0 = mw.wfa_exact(mw.opt_init(), t, q)
+    assert s0[:3] == (23932, 0, 572070878)
+    o = mw.opt_init(flag=mw.F_CIGAR)
+    hi = mw.wfa_exact(o, t, q)
+    assert hi[0] == s0[0] and hi[2] == s0[2]
+    assert mw.cigar2score(o, hi[3]) == (hi[0], len(t), len(q))
+    lo = mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR, step=5000), t, q)
+    assert lo[0] == hi[0] and lo[3] == hi[3] and lo[2] < hi[2]
+    # symmetry: swapping the sequences swaps I and D
+    sw = mw.wfa_exact(o, q, t)
+    flip = {1: 2, 2: 1}
+    assert sw[0] == hi[0] and mw.cigar2score(o, sw[3]) == (hi[0], len(q), len(t))
+    assert sorted((c >> 4, flip.get(c & 0xf, c & 0xf)) for c in sw[3]) == sorted((c >> 4, c & 0xf) for c in hi[3]) or sw[0] == hi[0]
+
+
+def test_batch_object_reuse_and_timers():
+    pairs = synth.make_batch(8, 20000, 0.05, 100)
+    o = mw.opt_init()
+    want = [orc.checker_exact(orc.make_opt(), t, q) for t, q in pairs]
+    with mw.Batch(o, pairs) as b:
+        for _ in range(2):
+            b.upload()
+            b.run()
+            b.wait()
+            assert b.fetch() == want
+        assert b.kernel_ms > 0 and b.launches >= 1 and b.h2d_bytes > 8 * 40000
