@@ -892,7 +892,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
 		long long worst = (max_sbound + 2) * (max_len + 16);
 		if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
-		worst = (worst + 255) & ~255LL;
+		worst = std::max((worst + 255) & ~255LL, 65536LL);
 		long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
 		if (per_slot < 4096) die("not enough free device memory for the traceback arena");
 		b->arena_total = per_slot * b->n_slots;
