@@ -210,7 +210,7 @@ def main():
     if local_rank == 0:
         ge.build()
     import miniwfa_b200 as mw
-    from miniwfa_b200 import synth
+    from miniwfa_b200 import synth, dist as mdist
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -291,6 +291,8 @@ def main():
             bb.upload()
             bb.run()
             rr = bb.fetch()
+            if world > 1:  # the one collective of the path: mwf_rst_t records of every shard -> rank 0
+                mdist.gather_to_root(list(range(rank * P, rank * P + P)), rr, P * world)
             return rr, bb.h2d_bytes, bb.d2h_bytes
 
     for _ in range(min(args.warmup, 2)):
