@@ -40,16 +40,20 @@ extern "C" {
 
 typedef struct mwf_b200_batch mwf_b200_batch_t;
 
-/* kernel families; AUTO picks per batch (many pairs -> one CTA per pair; few large pairs -> whole grid per pair) */
+/* kernel families; AUTO picks per batch:
+ *   TILE : temporally blocked -- ring tiles resident in shared memory for up to 64 scores (high-memory and score-only modes)
+ *   CTA  : streaming, one CTA per pair (small pairs, low-memory mode)
+ *   GRID : streaming, the whole grid on one pair (few large pairs in low-memory mode) */
 #define MWF_B200_KERNEL_AUTO 0
 #define MWF_B200_KERNEL_CTA  1
 #define MWF_B200_KERNEL_GRID 2
+#define MWF_B200_KERNEL_TILE 3
 
 int  mwf_b200_device_count(void);
 /* device used by batches created afterwards on any thread; default: $MWF_B200_DEVICE, else $LOCAL_RANK, else 0 */
 void mwf_b200_set_device(int dev);
 int  mwf_b200_get_device(void);
-/* force a kernel family (tests/bench); default: $MWF_B200_KERNEL ("cta"/"grid"), else AUTO */
+/* force a kernel family (tests/bench); default: $MWF_B200_KERNEL ("cta"/"grid"/"tile"), else AUTO */
 void mwf_b200_set_kernel(int kernel);
 /* threads per CTA for subsequently created batches (0 = default) */
 void mwf_b200_set_block_threads(int threads);
@@ -66,7 +70,7 @@ void mwf_b200_batch_destroy(mwf_b200_batch_t *b);
 /* measurements of the last mwf_b200_batch_run (valid after _wait) */
 double  mwf_b200_batch_kernel_ms(const mwf_b200_batch_t *b); /* CUDA-event time over the alignment kernels */
 int64_t mwf_b200_batch_launches(const mwf_b200_batch_t *b);  /* kernels launched by the last run */
-int     mwf_b200_batch_kernel_used(const mwf_b200_batch_t *b); /* MWF_B200_KERNEL_CTA or _GRID */
+int     mwf_b200_batch_kernel_used(const mwf_b200_batch_t *b); /* MWF_B200_KERNEL_CTA, _GRID or _TILE */
 int64_t mwf_b200_batch_h2d_bytes(const mwf_b200_batch_t *b);
 int64_t mwf_b200_batch_d2h_bytes(const mwf_b200_batch_t *b);
 

@@ -7,9 +7,9 @@ There is no CPU implementation here; loading fails loudly if the library is miss
 """
 from .api import (MwfOpt, MwfRst, Batch, opt_init, wfa_exact, wfa_auto, wfa_exact_batch,
                   cigar_string, cigar2score, device_count, set_device, set_kernel, lib,
-                  F_CIGAR, F_NO_KALLOC, KERNEL_AUTO, KERNEL_CTA, KERNEL_GRID)
+                  F_CIGAR, F_NO_KALLOC, KERNEL_AUTO, KERNEL_CTA, KERNEL_GRID, KERNEL_TILE)
 from . import synth
 
 __all__ = ["MwfOpt", "MwfRst", "Batch", "opt_init", "wfa_exact", "wfa_auto", "wfa_exact_batch",
            "cigar_string", "cigar2score", "device_count", "set_device", "set_kernel", "lib", "synth",
-           "F_CIGAR", "F_NO_KALLOC", "KERNEL_AUTO", "KERNEL_CTA", "KERNEL_GRID"]
+           "F_CIGAR", "F_NO_KALLOC", "KERNEL_AUTO", "KERNEL_CTA", "KERNEL_GRID", "KERNEL_TILE"]

@@ -8,7 +8,7 @@ import os
 
 F_CIGAR = 0x1
 F_NO_KALLOC = 0x2
-KERNEL_AUTO, KERNEL_CTA, KERNEL_GRID = 0, 1, 2
+KERNEL_AUTO, KERNEL_CTA, KERNEL_GRID, KERNEL_TILE = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libminiwfa_b200.so")

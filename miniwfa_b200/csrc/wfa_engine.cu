@@ -709,6 +709,8 @@ __global__ void __launch_bounds__(512, 1) wfa_grid_kernel(const KParams P)
 	run_pair(g, P, P.single_pair, 0, smem);
 }
 
+#include "wfa_tile.cuh"
+
 /* ------------------------------------------------------------------------------------------ */
 /* host side                                                                                   */
 /* ------------------------------------------------------------------------------------------ */
@@ -754,6 +756,7 @@ static int pick_kernel_pref(void)
 		k = MWF_B200_KERNEL_AUTO;
 		if (v && !strcmp(v, "cta")) k = MWF_B200_KERNEL_CTA;
 		else if (v && !strcmp(v, "grid")) k = MWF_B200_KERNEL_GRID;
+		else if (v && !strcmp(v, "tile")) k = MWF_B200_KERNEL_TILE;
 	}
 	return k;
 }
@@ -785,6 +788,15 @@ struct mwf_b200_batch {
 	double kernel_ms;
 	int64_t launches, h2d, d2h;
 	bool ran;
+	/* tile engine (wfa_tile.cuh) */
+	int tW, tHL, tT, tR, tNT, wave_pairs, tile_grid;
+	size_t tile_smem, items_cap;
+	TileCtl *d_tctl;
+	int32_t *d_state, *d_alive;
+	int2 *d_items;
+	unsigned char *d_tmisc; /* TileCounters[2] @0, n_running @32, arena_used @64 */
+	int *h_running;
+	cudaEvent_t evc[2];
 };
 
 static void die(const char *msg)
@@ -850,8 +862,22 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 
 	/* kernel family */
 	int pref = pick_kernel_pref();
-	if (pref == MWF_B200_KERNEL_AUTO)
-		pref = (n_pairs >= b->n_sm / 4 || max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
+	const int n = b->pen.nring;
+	b->tT = env_int("MWF_B200_TILE_T", 64) & ~3;
+	b->tT = std::max(4, std::min(b->tT, TILE_TMAX));
+	b->tHL = b->tT;
+	b->tNT = env_int("MWF_B200_TILE_THREADS", 256);
+	b->tW = 4 * b->tNT;
+	b->tR = n + 2 * (opt->e1 + 1) + 2 * (opt->e2 + 1);
+	b->tile_smem = (size_t)b->tR * b->tW * 4 + 64 + 8 * TILE_TMAX;
+	const int umax = b->tW - 2 * b->tHL;
+	const bool tile_ok = !seg && n <= 64 && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 &&
+		b->tile_smem <= (size_t)prop.sharedMemPerBlockOptin && umax / 2 - 4 >= 2 * b->tHL + n + 8;
+	if (pref == MWF_B200_KERNEL_TILE && !tile_ok) pref = MWF_B200_KERNEL_AUTO;
+	if (pref == MWF_B200_KERNEL_AUTO) {
+		if (tile_ok && max_len >= env_int("MWF_B200_TILE_MINLEN", 8192)) pref = MWF_B200_KERNEL_TILE;
+		else pref = (n_pairs >= b->n_sm / 4 || max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
+	}
 	b->kernel = pref;
 	b->n_slots = pref == MWF_B200_KERNEL_GRID ? 1 : std::max(1, std::min(n_pairs, b->n_sm));
 
@@ -861,9 +887,6 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	CUDA_OK(cudaEventCreate(&b->ev1));
 
 	/* device workspaces */
-	const int n = b->pen.nring;
-	b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
-	b->ring_stride = (long long)n * 5 * b->pitch;
 	CUDA_OK(cudaMalloc(&b->d_seq, b->seq_bytes));
 	CUDA_OK(cudaMallocHost(&b->h_seq, b->seq_bytes));
 	memset(b->h_seq, 0, b->seq_bytes);
@@ -872,31 +895,77 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	CUDA_OK(cudaMallocHost(&b->h_outs, sizeof(PairOut) * std::max(1, n_pairs)));
 	CUDA_OK(cudaMalloc(&b->d_order, sizeof(int) * std::max(1, n_pairs)));
 	CUDA_OK(cudaMalloc(&b->d_ctl, 64));
-	CUDA_OK(cudaMalloc(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots));
-	b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
-	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0;
-	if (b->is_tb) {
-		CUDA_OK(cudaMalloc(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw)));
-		b->rowtab_stride = max_sbound + 2;
-		CUDA_OK(cudaMalloc(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots));
-		if (seg) {
-			CUDA_OK(cudaMalloc(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots));
-			b->snap_cap = (int)(max_sbound / opt->step + 2);
-			CUDA_OK(cudaMalloc(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots));
-			CUDA_OK(cudaMalloc(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots));
-			CUDA_OK(cudaMalloc(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots));
-		}
-		/* traceback / snapshot arena: the worst case when it is small, else most of what is free */
+	b->d_ring = 0, b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_tmisc = 0, b->h_running = 0;
+	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0, b->wave_pairs = 0;
+	if (b->is_tb) CUDA_OK(cudaMalloc(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw)));
+	if (pref == MWF_B200_KERNEL_TILE) {
+		/* state: two buffers of R rows per pair in flight; pairs beyond the memory budget run in later waves */
+		b->pitch = (int)((max_len + 2LL * n + 2LL * b->tHL + 32 + b->tW + 31) & ~31LL);
+		b->rowtab_stride = b->is_tb ? max_sbound + 2 : 0;
+		const size_t per_pair = (size_t)b->pitch * 4 * (2 * b->tR + 1) + sizeof(TileCtl) + (size_t)b->rowtab_stride * 8 +
+			sizeof(int2) * ((size_t)b->pitch / umax + 2);
 		size_t free_b = 0, total_b = 0;
 		CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-		const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
-		long long worst = (max_sbound + 2) * (max_len + 16);
-		if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
-		worst = std::max((worst + 255) & ~255LL, 65536LL);
-		long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
-		if (per_slot < 4096) die("not enough free device memory for the traceback arena");
-		b->arena_total = per_slot * b->n_slots;
-		CUDA_OK(cudaMalloc(&b->d_arena, (size_t)b->arena_total));
+		const double frac = b->is_tb ? 0.35 : 0.85;
+		b->wave_pairs = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_pairs), (size_t)(free_b * frac) / per_pair));
+		const int wp = b->wave_pairs;
+		CUDA_OK(cudaMalloc(&b->d_state, (size_t)wp * 2 * b->tR * b->pitch * 4));
+		CUDA_OK(cudaMemsetAsync(b->d_state, 0xC0, (size_t)wp * 2 * b->tR * b->pitch * 4, b->stream)); /* a large negative int32 everywhere */
+		CUDA_OK(cudaMalloc(&b->d_alive, (size_t)wp * b->pitch * 4));
+		CUDA_OK(cudaMalloc(&b->d_tctl, sizeof(TileCtl) * wp));
+		b->items_cap = (size_t)wp * ((size_t)b->pitch / umax + 2);
+		CUDA_OK(cudaMalloc(&b->d_items, sizeof(int2) * b->items_cap));
+		CUDA_OK(cudaMalloc(&b->d_tmisc, 128));
+		CUDA_OK(cudaMallocHost(&b->h_running, 2 * sizeof(int)));
+		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
+		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
+		if (b->is_tb) {
+			CUDA_OK(cudaMalloc(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * wp));
+			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
+			long long worst = (max_sbound + 2) * (max_len + 2LL * n + 2LL * b->tT + 16);
+			worst = std::max((worst + 255) & ~255LL, 65536LL);
+			b->arena_total = (long long)std::min((double)budget, (double)worst * wp) & ~255LL;
+			if (b->arena_total < 4096) die("not enough free device memory for the traceback arena");
+			CUDA_OK(cudaMalloc(&b->d_arena, (size_t)b->arena_total));
+		}
+		int per_sm = 0;
+		if (b->is_tb) {
+			CUDA_OK(cudaFuncSetAttribute(wfa_tile_kernel<MODE_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem));
+			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfa_tile_kernel<MODE_TB>, b->tNT, b->tile_smem));
+		} else {
+			CUDA_OK(cudaFuncSetAttribute(wfa_tile_kernel<MODE_SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem));
+			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfa_tile_kernel<MODE_SCORE>, b->tNT, b->tile_smem));
+		}
+		if (per_sm < 1) die("tile kernel does not fit on an SM");
+		b->tile_grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
+	} else {
+		b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
+		b->ring_stride = (long long)n * 5 * b->pitch;
+		CUDA_OK(cudaMalloc(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots));
+		if (b->is_tb) {
+			b->rowtab_stride = max_sbound + 2;
+			CUDA_OK(cudaMalloc(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots));
+			if (seg) {
+				CUDA_OK(cudaMalloc(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots));
+				b->snap_cap = (int)(max_sbound / opt->step + 2);
+				CUDA_OK(cudaMalloc(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots));
+				CUDA_OK(cudaMalloc(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots));
+				CUDA_OK(cudaMalloc(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots));
+			}
+			/* traceback / snapshot arena: the worst case when it is small, else most of what is free */
+			size_t free_b = 0, total_b = 0;
+			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
+			long long worst = (max_sbound + 2) * (max_len + 16);
+			if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
+			worst = std::max((worst + 255) & ~255LL, 65536LL);
+			long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
+			if (per_slot < 4096) die("not enough free device memory for the traceback arena");
+			b->arena_total = per_slot * b->n_slots;
+			CUDA_OK(cudaMalloc(&b->d_arena, (size_t)b->arena_total));
+		}
 	}
 	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false;
 	return b;
@@ -904,7 +973,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 
 extern "C" void mwf_b200_batch_set_stream(mwf_b200_batch_t *b, void *cuda_stream)
 {
-	if (b->own_stream) { CUDA_OK(cudaStreamDestroy(b->stream)); b->own_stream = false; }
+	if (b->own_stream) { CUDA_OK(cudaStreamSynchronize(b->stream)); CUDA_OK(cudaStreamDestroy(b->stream)); b->own_stream = false; }
 	b->stream = (cudaStream_t)cuda_stream;
 }
 
@@ -963,13 +1032,69 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
 	++b->launches;
 }
 
+/* the tile engine's host loop: plan + tile kernels per time block, until every pair of the wave has ended.
+ * The number of running pairs is read back one chunk of launches behind, so the device never waits for the host. */
+static void run_tile(mwf_b200_batch_t *b)
+{
+	TParams P;
+	memset(&P, 0, sizeof(P));
+	P.pen = b->pen, P.is_tb = b->is_tb, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter;
+	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.cigar = b->d_cigar;
+	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
+	P.pitch = b->pitch, P.R = b->tR, P.W = b->tW, P.HL = b->tHL, P.T = b->tT;
+	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32);
+	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
+	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
+	P.seg = 0, P.seg_stride = 0;
+	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
+	for (int p0 = 0; p0 < b->n; p0 += b->wave_pairs) {
+		const int np = std::min(b->wave_pairs, b->n - p0);
+		P.pair0 = p0, P.n_pairs = np;
+		CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
+		CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
+		wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(P);
+		CUDA_OK(cudaGetLastError());
+		++b->launches;
+		int it = 0;
+		for (int chunk = 0;; ++chunk) {
+			for (int k = 0; k < chunk_len; ++k, ++it) {
+				wfa_plan_kernel<<<np, 128, 0, b->stream>>>(P, it);
+				if (b->is_tb) wfa_tile_kernel<MODE_TB><<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
+				else wfa_tile_kernel<MODE_SCORE><<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
+				b->launches += 2;
+			}
+			CUDA_OK(cudaGetLastError());
+			if (env_int("MWF_B200_DEBUG", 0)) {
+				TileCtl h;
+				CUDA_OK(cudaStreamSynchronize(b->stream));
+				CUDA_OK(cudaMemcpy(&h, b->d_tctl, sizeof(h), cudaMemcpyDeviceToHost));
+				fprintf(stderr, "[tile dbg] it=%d status=%d s=%d band=[%d,%d] cur=%d n_iter=%lld Tb=%d A4=%d total4=%d n_tiles=%d done_t=%d fin=[%d,%d] lo0=%d hi0=%d\n",
+				        it, h.status, h.s, h.wflo, h.wfhi, h.cur, h.n_iter, h.Tb, h.A4, h.total4, h.n_tiles, h.done_t, h.fin_lo, h.fin_hi, h.lo_log[0], h.hi_log[0]);
+			}
+			CUDA_OK(cudaMemcpyAsync(&b->h_running[chunk & 1], P.n_running, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+			CUDA_OK(cudaEventRecord(b->evc[chunk & 1], b->stream));
+			if (chunk >= 1) {
+				CUDA_OK(cudaEventSynchronize(b->evc[(chunk - 1) & 1]));
+				if (b->h_running[(chunk - 1) & 1] == 0) break;
+			}
+		}
+		if (b->is_tb) {
+			wfa_tile_traceback_kernel<<<np, 32, 0, b->stream>>>(P);
+			CUDA_OK(cudaGetLastError());
+			++b->launches;
+		}
+	}
+}
+
 extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 {
 	CUDA_OK(cudaSetDevice(b->dev));
 	b->launches = 0;
 	CUDA_OK(cudaEventRecord(b->ev0, b->stream));
 	if (b->n > 0) {
-		if (b->kernel == MWF_B200_KERNEL_CTA) {
+		if (b->kernel == MWF_B200_KERNEL_TILE) {
+			run_tile(b);
+		} else if (b->kernel == MWF_B200_KERNEL_CTA) {
 			launch_cta(b, make_params(b, b->n_slots), b->n_slots);
 		} else {
 			const KParams P = make_params(b, 1);
@@ -1046,6 +1171,8 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	cudaFree(b->d_seq); cudaFreeHost(b->h_seq); cudaFree(b->d_pairs); cudaFree(b->d_outs); cudaFreeHost(b->h_outs);
 	cudaFree(b->d_order); cudaFree(b->d_ctl); cudaFree(b->d_ring); cudaFree(b->d_ring2); cudaFree(b->d_arena);
 	cudaFree(b->d_rowtab); cudaFree(b->d_snapoff); cudaFree(b->d_snaphdr); cudaFree(b->d_seg); cudaFree(b->d_cigar);
+	cudaFree(b->d_tctl); cudaFree(b->d_state); cudaFree(b->d_alive); cudaFree(b->d_items); cudaFree(b->d_tmisc);
+	if (b->h_running) { cudaFreeHost(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
 	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
 	if (b->own_stream) cudaStreamDestroy(b->stream);
 	delete b;

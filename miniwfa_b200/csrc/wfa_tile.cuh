@@ -1,0 +1,514 @@
+/*
+ * wfa_tile.cuh -- the temporally blocked ("tile") engine: wf_next + wf_extend for T scores at a
+ * time with the wavefront ring resident in shared memory.  Included by wfa_engine.cu.
+ *
+ * Reference (/root/reference/miniwfa.c @ 66770a3): the per-score loop of mwf_wfa_core (:397-426):
+ * extend loop + wf_extend1_padded (:400-411, :212-226), wf_next_basic/prep/score/tb (:243-327),
+ * wf_stripe_shrink (:144-171), the stop tests (:421-425), the checkpoint collapse (:413-416).
+ *
+ * Why: one score step reads 7 and writes 5 int32 per diagonal; with the ring in HBM that is 48-64 B per
+ * cell and one barrier per score.  Here a *time block* advances a pair by Tb <= T scores:
+ *   - the diagonals the block can touch, [wflo-Tb-nring, wfhi+Tb+nring], are cut into tiles;
+ *   - a CTA bulk-copies (cp.async.bulk, mbarrier) the tile plus a halo of HL >= Tb diagonals on each side
+ *     -- all R = nring + 2(e1+1) + 2(e2+1) live ring rows (27 for the default penalties, not the
+ *     reference's 85) -- from the pair's state buffer into shared memory, runs Tb fused next+extend
+ *     steps with one __syncthreads each, and bulk-copies the useful columns to the other state buffer;
+ *   - halo columns go stale by one diagonal per step and are never stored.
+ * HBM traffic drops to ~ (W+U)/(U*Tb) * 4R bytes per cell (3-7 B) plus 1 B/cell of traceback.
+ *
+ * Exactness of the band (n_iter, max_iter stop): the first and the last tile of a block replay the
+ * reference's lo/hi rule (:325-326, :417-418) step by step, force every cell outside [lo_t, hi_t] to
+ * NEG_INF (what the reference's pads hold, :96-99) and log lo_t, hi_t; wfa_plan_kernel then replays the
+ * block score by score (n_iter, stop tests, termination), trims the band at multiples of 256 from
+ * per-diagonal "alive" words the tiles accumulate over the last nring scores, and cuts the next block.
+ *
+ * Kernels: wfa_tile_init_kernel (score 0), wfa_plan_kernel (one CTA per pair, between blocks),
+ * wfa_tile_kernel<MODE> (persistent CTAs pulling (pair, tile) items), wfa_tile_traceback_kernel.
+ */
+#ifndef WFA_TILE_CUH
+#define WFA_TILE_CUH
+
+#define TILE_TMAX 64
+
+enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4 };
+
+struct TileCtl { /* per pair, lives in HBM for the whole run */
+	int status, s, wflo, wfhi, cur, last, sid, n_seg;
+	long long n_iter;
+	/* the block in flight */
+	int Tb, A4, total4, n_tiles;
+	int done_t, done_last, fin_lo, fin_hi;
+	int lo_log[TILE_TMAX], hi_log[TILE_TMAX];
+};
+
+struct TileCounters { unsigned int n_items, next; };
+
+struct TParams {
+	Pen pen;
+	int is_tb, max_s;
+	long long max_iter;
+	int n_pairs, pair0;        /* this wave: pairs order[pair0 .. pair0+n_pairs) */
+	const int *order;
+	const PairDesc *pairs;
+	PairOut *outs;
+	const uint8_t *seq;
+	uint32_t *cigar;
+	TileCtl *ctl;              /* [n_pairs] */
+	int32_t *state;            /* [n_pairs][2][R][pitch] */
+	int32_t *alive;            /* [n_pairs][pitch] */
+	int pitch, R, W, HL, T;
+	int2 *items;
+	TileCounters *cnt;         /* [2] */
+	int *n_running;
+	uint8_t *arena;
+	long long arena_cap;
+	unsigned long long *arena_used;
+	long long *rowtab;         /* [n_pairs][rowtab_stride] */
+	long long rowtab_stride;
+	const int *seg;            /* pass-2 checkpoints (s,d) per pair, or null */
+	int seg_stride;
+};
+
+__device__ __forceinline__ int tile_doff(const TParams &P, int tl) { return tl + P.pen.nring + P.HL + 8; }
+
+/* row index inside a state buffer / the shared-memory tile */
+struct RowMap {
+	int nring, d1, d2, bE1, bF1, bE2, bF2;
+	__device__ __forceinline__ RowMap(const Pen &p)
+	{
+		nring = p.nring, d1 = p.e1 + 1, d2 = p.e2 + 1;
+		bE1 = nring, bF1 = bE1 + d1, bE2 = bF1 + d1, bF2 = bE2 + d2;
+	}
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* bulk-copy (TMA, non-tensor form) + mbarrier helpers                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+	             :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* score 0 (wf_stripe_init, miniwfa.c:103-121, and the first extend)                            */
+/* ------------------------------------------------------------------------------------------ */
+
+__global__ void wfa_tile_init_kernel(const TParams P)
+{
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	const PairDesc pd = P.pairs[pi];
+	const int n = P.pen.nring, doff = tile_doff(P, pd.tl);
+	int32_t *st = P.state + (size_t)slot * 2 * P.R * P.pitch;
+	const int span = 2 * (n + 2) + 1; /* every slice reads as NEG_INF around diagonal 0 */
+	for (int t = threadIdx.x; t < P.R * span; t += blockDim.x) {
+		const int row = t / span, c = t % span;
+		st[(size_t)row * P.pitch + doff - (n + 2) + c] = NEG_INF;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const uint32_t *T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), *Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off);
+		const int k = extend_run(T, Q, -1, 0, min(pd.tl - 1, pd.ql - 1));
+		st[doff] = k; /* H of score 0 lives in slot 0 */
+		TileCtl *c = P.ctl + slot;
+		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->n_seg = 0, c->n_iter = 0;
+		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0;
+		c->status = (k == pd.tl - 1 && k == pd.ql - 1) ? TS_DONE : TS_RUN;
+		if (c->status == TS_DONE) {
+			PairOut o;
+			o.s = 0, o.n_cigar = 0, o.n_iter = 0, o.cigar_pos = pd.cigar_off + pd.cigar_cap, o.status = ST_OK, o.pad_ = 0;
+			P.outs[pi] = o;
+		} else atomicAdd(P.n_running, 1);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* between blocks: replay the finished block, trim, cut the next one                            */
+/* ------------------------------------------------------------------------------------------ */
+
+__global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
+{
+	__shared__ int sh[4];
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	TileCtl *c = P.ctl + slot;
+	if (blockIdx.x == 0 && threadIdx.x == 0) { P.cnt[(it + 1) & 1].n_items = 0; P.cnt[(it + 1) & 1].next = 0; }
+	if (c->status != TS_RUN) return;
+	const PairDesc pd = P.pairs[pi];
+	const int tl = pd.tl, ql = pd.ql, n = P.pen.nring, doff = tile_doff(P, tl);
+	int status = TS_RUN, s = c->s, wflo = c->wflo, wfhi = c->wfhi;
+	if (c->Tb > 0) { /* replay, in the order of miniwfa.c:419-426 */
+		if (threadIdx.x == 0) {
+			long long n_iter = c->n_iter;
+			const int Tb = c->Tb, s0 = c->s;
+			int last = 0;
+			for (int t = 1; t <= Tb; ++t) {
+				n_iter += c->hi_log[t - 1] - c->lo_log[t - 1] + 1;
+				s = s0 + t;
+				if ((P.max_iter > 0 && n_iter > P.max_iter) || (P.max_s > 0 && s > P.max_s)) { status = TS_STOPPED; break; }
+				if (c->done_t == t) { status = TS_DONE; last = c->done_last; break; }
+			}
+			c->n_iter = n_iter, c->s = s, c->last = last;
+			c->wflo = c->fin_lo, c->wfhi = c->fin_hi, c->cur ^= 1;
+			sh[0] = status, sh[1] = s;
+		}
+		__syncthreads();
+		status = sh[0], s = sh[1], wflo = c->fin_lo, wfhi = c->fin_hi;
+		__syncthreads();
+		if (status == TS_RUN && (s & 0xff) == 0) { /* wf_stripe_shrink (:144-171) from the tiles' alive words */
+			const int32_t *alive = P.alive + (size_t)slot * P.pitch + doff;
+			const int tag = s | 1, lane = threadIdx.x & 31;
+			if (threadIdx.x < 32) {
+				int nl = wfhi + 1;
+				for (int base = wflo; base <= wfhi; base += 32) {
+					const int d = base + lane;
+					const unsigned m = __ballot_sync(0xffffffffu, d <= wfhi && alive[d] == tag);
+					if (m) { nl = base + __ffs(m) - 1; break; }
+				}
+				int nh = nl - 1;
+				for (int base = wfhi; base >= nl; base -= 32) {
+					const int d = base - lane;
+					const unsigned m = __ballot_sync(0xffffffffu, d >= nl && alive[d] == tag);
+					if (m) { nh = base - (__ffs(m) - 1); break; }
+				}
+				if (lane == 0) sh[2] = nl, sh[3] = nh;
+			}
+			__syncthreads();
+			const int nl = sh[2], nh = sh[3];
+			if (nl > wfhi || nh < nl) status = TS_SHRINK; /* the reference asserts (:157, :169) */
+			else wflo = nl, wfhi = nh;
+		}
+	}
+	if (threadIdx.x != 0) return;
+	if (status == TS_RUN) { /* cut the next block */
+		int sid = c->sid;
+		if (P.seg && sid < c->n_seg && P.seg[(size_t)slot * P.seg_stride + 2 * sid] == s) { /* band collapse (:413-416) */
+			wflo = wfhi = P.seg[(size_t)slot * P.seg_stride + 2 * sid + 1];
+			++sid;
+		}
+		int Tb = min(P.T, ((s | 0xff) + 1) - s);
+		if (P.seg && sid < c->n_seg) Tb = min(Tb, P.seg[(size_t)slot * P.seg_stride + 2 * sid] - s);
+		if (P.max_s > 0) Tb = min(Tb, P.max_s + 1 - s);
+		if (P.is_tb) Tb = min(Tb, (int)P.rowtab_stride - 1 - s); /* no score lies beyond the all-gap alignment */
+		Tb = max(Tb, 1);
+		const int lo_sup = max(wflo - Tb, -tl) - n, hi_sup = min(wfhi + Tb, ql) + n;
+		const int A4 = (lo_sup + doff) & ~3, Bx = (hi_sup + doff) | 3;
+		const int total4 = (Bx - A4 + 1) >> 2, umax = P.W - 2 * P.HL;
+		const int n_tiles = (total4 * 4 + umax - 1) / umax;
+		if (P.is_tb) { /* wf_tb_add (:33-44): one row per score, here as wide as the block's superset */
+			const long long rowsize = Bx - A4 + 1;
+			const unsigned long long base = atomicAdd(P.arena_used, (unsigned long long)(rowsize * Tb));
+			if ((long long)base + rowsize * Tb > P.arena_cap || s + Tb >= P.rowtab_stride) status = TS_ARENA;
+			else {
+				long long *rt = P.rowtab + (size_t)slot * P.rowtab_stride;
+				for (int t = 1; t <= Tb; ++t) rt[s + t] = (long long)base + (long long)(t - 1) * rowsize - A4;
+			}
+		}
+		if (status == TS_RUN) {
+			c->wflo = wflo, c->wfhi = wfhi, c->sid = sid;
+			c->Tb = Tb, c->A4 = A4, c->total4 = total4, c->n_tiles = n_tiles;
+			c->done_t = 0x7fffffff, c->done_last = 0;
+			const unsigned int base = atomicAdd(&P.cnt[it & 1].n_items, (unsigned int)n_tiles);
+			for (int j = 0; j < n_tiles; ++j) P.items[base + j] = make_int2(slot, j);
+		}
+	}
+	if (status != TS_RUN) {
+		c->status = status;
+		atomicSub(P.n_running, 1);
+		PairOut o;
+		o.s = status == TS_DONE ? c->s : -1;
+		o.n_cigar = 0, o.n_iter = c->n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap;
+		o.status = status == TS_DONE ? ST_OK : status == TS_STOPPED ? ST_STOPPED : status == TS_ARENA ? ST_ARENA : ST_SHRINK;
+		o.pad_ = 0;
+		P.outs[pi] = o;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* the tile kernel                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+struct TileRows { /* shared-memory row bases (int32 index into the tile), for one score */
+	int Hx, Ho1, Ho2, pE1, pF1, pE2, pF2, nH, nE1, nF1, nE2, nF2;
+};
+
+__device__ __forceinline__ int wrap_sub(int a, int b, int m) { int r = a - b; return r < 0 ? r + m : r; }
+
+/* one score step for the 4 diagonals of this thread.  EDGE = false: the whole warp lies strictly inside the
+ * band and does not hold the terminal diagonal, so no masking, no edge rule, no termination test. */
+template<int MODE, bool EDGE>
+__device__ __forceinline__ int tile_cells(int32_t *rows, const TileRows &r, int c, int W, int d0, int lo_t, int hi_t, int dfin, int tl,
+                                          const int (&kmin)[4], const int (&kspan)[4], const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
+                                          bool first_thread, bool last_thread, bool useful, uint32_t &tbw_out, int4 &newH,
+                                          int4 &vE1o, int4 &vF1o, int4 &vE2o, int4 &vF2o)
+{
+	const int lane = threadIdx.x & 31;
+	const int4 ho1 = *reinterpret_cast<const int4*>(rows + r.Ho1 + c), pe1 = *reinterpret_cast<const int4*>(rows + r.pE1 + c);
+	const int4 pf1 = *reinterpret_cast<const int4*>(rows + r.pF1 + c), ho2 = *reinterpret_cast<const int4*>(rows + r.Ho2 + c);
+	const int4 pe2 = *reinterpret_cast<const int4*>(rows + r.pE2 + c), pf2 = *reinterpret_cast<const int4*>(rows + r.pF2 + c);
+	const int4 hx = *reinterpret_cast<const int4*>(rows + r.Hx + c);
+	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int o1 = I4(ho1, j), o2 = I4(ho2, j), e1 = I4(pe1, j), e2 = I4(pe2, j), f1 = I4(pf1, j), f2 = I4(pf2, j);
+		A1[j + 1] = max(o1, e1), A2[j + 1] = max(o2, e2);
+		C1[j + 1] = max(o1, f1) + 1, C2[j + 1] = max(o2, f2) + 1;
+		if (MODE != MODE_SCORE) bA1[j + 1] = o1 < e1, bA2[j + 1] = o2 < e2, bC1[j + 1] = o1 < f1, bC2[j + 1] = o2 < f2;
+	}
+	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
+	A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
+	C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+	C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	if (MODE != MODE_SCORE) {
+		const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
+		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+	}
+	if (lane == 0) { /* left neighbour belongs to another warp (or to nobody: stale halo) */
+		int o1 = NEG_INF, e1 = NEG_INF, o2 = NEG_INF, e2 = NEG_INF;
+		if (!first_thread) o1 = rows[r.Ho1 + c - 1], e1 = rows[r.pE1 + c - 1], o2 = rows[r.Ho2 + c - 1], e2 = rows[r.pE2 + c - 1];
+		A1[0] = max(o1, e1), A2[0] = max(o2, e2);
+		if (MODE != MODE_SCORE) bA1[0] = o1 < e1, bA2[0] = o2 < e2;
+	}
+	if (lane == 31) {
+		int o1 = NEG_INF, f1 = NEG_INF, o2 = NEG_INF, f2 = NEG_INF;
+		if (!last_thread) o1 = rows[r.Ho1 + c + 4], f1 = rows[r.pF1 + c + 4], o2 = rows[r.Ho2 + c + 4], f2 = rows[r.pF2 + c + 4];
+		C1[5] = max(o1, f1) + 1, C2[5] = max(o2, f2) + 1;
+		if (MODE != MODE_SCORE) bC1[5] = o1 < f1, bC2[5] = o2 < f2;
+	}
+	int vH[4], vE1[4], vF1[4], vE2[4], vF2[4], st[4];
+	bool ext[4];
+	uint32_t tbw = 0;
+	int myfl = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2], F2 = C2[j + 2];
+		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = I4(hx, j) + 1;
+		int H = max(hxp, gmx);
+		if (MODE != MODE_SCORE) { /* the 7-bit pack, miniwfa.c:290-306 */
+			const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4));
+			st[j] = z;
+			tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j);
+		}
+		if (EDGE) {
+			const int d = d0 + j;
+			if (d < lo_t || d > hi_t) H = E1 = E2 = F1 = F2 = NEG_INF; /* outside the slice: what the reference's pads hold */
+			else if (H >= -1 || E1 >= -1 || F1 >= -1 || E2 >= -1 || F2 >= -1) { /* edge rule, :325-326 */
+				if (d == lo_t) myfl |= FL_LO;
+				if (d == hi_t) myfl |= FL_HI;
+			}
+		}
+		vE1[j] = E1, vE2[j] = E2, vF1[j] = F1, vF2[j] = F2, vH[j] = H;
+		ext[j] = (unsigned)(H - kmin[j]) <= (unsigned)kspan[j]; /* on the matrix (:402) */
+	}
+	uint32_t px[4];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) { /* first probe of the match run, all four loads in flight together */
+		const int tp = ext[j] ? vH[j] + 1 : 0, qp = ext[j] ? d0 + j + vH[j] + 1 : 0;
+		px[j] = seq_word(T, tp) ^ seq_word(Q, qp);
+	}
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		if (!ext[j]) continue;
+		const int h0 = vH[j], kmax = kmin[j] + kspan[j];
+		int k;
+		if (px[j]) k = min(h0 + ((__ffs(px[j]) - 1) >> 3), kmax);
+		else k = extend_run(T, Q, min(h0 + 4, kmax), d0 + j, kmax);
+		if (EDGE && useful && d0 + j == dfin && k == tl - 1) { /* end of both sequences, :405-409 */
+			myfl |= FL_DONE;
+			if (MODE == MODE_TB && k == h0) myfl |= st[j] << FL_LAST_SHIFT;
+		}
+		vH[j] = k;
+	}
+	*reinterpret_cast<int4*>(rows + r.nH + c) = make_int4(vH[0], vH[1], vH[2], vH[3]);
+	*reinterpret_cast<int4*>(rows + r.nE1 + c) = make_int4(vE1[0], vE1[1], vE1[2], vE1[3]);
+	*reinterpret_cast<int4*>(rows + r.nF1 + c) = make_int4(vF1[0], vF1[1], vF1[2], vF1[3]);
+	*reinterpret_cast<int4*>(rows + r.nE2 + c) = make_int4(vE2[0], vE2[1], vE2[2], vE2[3]);
+	*reinterpret_cast<int4*>(rows + r.nF2 + c) = make_int4(vF2[0], vF2[1], vF2[2], vF2[3]);
+	tbw_out = tbw;
+	newH = make_int4(vH[0], vH[1], vH[2], vH[3]);
+	vE1o = make_int4(vE1[0], vE1[1], vE1[2], vE1[3]), vF1o = make_int4(vF1[0], vF1[1], vF1[2], vF1[3]);
+	vE2o = make_int4(vE2[0], vE2[1], vE2[2], vE2[3]), vF2o = make_int4(vF2[0], vF2[1], vF2[2], vF2[3]);
+	return myfl;
+}
+
+__device__ __forceinline__ bool on_matrix_u(int d, int k, int tl, int ql)
+{
+	return (unsigned)(k + 1) <= (unsigned)tl && (unsigned)(d + k + 1) <= (unsigned)ql;
+}
+
+/* shared memory: rows[R][W] int32 | ctl ints [16] | mbarrier | rowoff[TILE_TMAX] */
+template<int MODE>
+__global__ void __launch_bounds__(512) wfa_tile_kernel(const TParams P, int it)
+{
+	extern __shared__ __align__(128) int32_t smem_tile[];
+	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
+	int32_t *rows = smem_tile;
+	int *sc = rows + (size_t)R * W;                          /* [0..2] flags, [3] item */
+	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8);
+	long long *rowoff = reinterpret_cast<long long*>(sc + 16);
+	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+	const Pen pen = P.pen;
+	const RowMap rm(pen);
+	const int n = pen.nring;
+	const unsigned int n_items = P.cnt[it & 1].n_items;
+	if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	uint32_t phase = 0;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) sc[3] = (int)atomicAdd(&P.cnt[it & 1].next, 1u);
+		__syncthreads();
+		const unsigned int item = (unsigned int)sc[3];
+		if (item >= n_items) break;
+		const int2 it2 = P.items[item];
+		const int slot = it2.x, tile = it2.y;
+		TileCtl *ctl = P.ctl + slot;
+		const int pi = P.order[P.pair0 + slot];
+		const PairDesc pd = P.pairs[pi];
+		const int tl = pd.tl, ql = pd.ql, doff = tile_doff(P, tl), dfin = ql - tl;
+		const int Tb = ctl->Tb, s0 = ctl->s, n_tiles = ctl->n_tiles, cur = ctl->cur;
+		const int u0 = (int)((long long)tile * ctl->total4 / n_tiles), u1 = (int)((long long)(tile + 1) * ctl->total4 / n_tiles);
+		const int ustart = ctl->A4 + 4 * u0, ulen = 4 * (u1 - u0), idx0 = ustart - HL;
+		const bool left_edge = tile == 0, right_edge = tile == n_tiles - 1;
+		int wflo_c = ctl->wflo, wfhi_c = ctl->wfhi;
+		int32_t *st_in = P.state + ((size_t)slot * 2 + cur) * R * pitch;
+		int32_t *st_out = P.state + ((size_t)slot * 2 + (cur ^ 1)) * R * pitch;
+		/* ---- load the tile: R rows of W int32, one bulk copy per row ---- */
+		if (tid < 32) {
+			fence_async_smem();
+			if (tid == 0) mbar_expect_tx(bar, (uint32_t)(R * W * 4));
+			__syncwarp();
+			for (int r = tid; r < R; r += 32)
+				bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
+		}
+		if (MODE == MODE_TB && tid < Tb) rowoff[tid] = P.rowtab[(size_t)slot * P.rowtab_stride + s0 + 1 + tid];
+		if (tid < 3) sc[tid] = 0;
+		const uint32_t *T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), *Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off);
+		const int c = 4 * tid, d0 = idx0 + c - doff;
+		const bool useful = c >= HL && c < HL + ulen;
+		int kmin[4], kspan[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { /* H is on the matrix iff kmin <= H <= kmin + kspan (:402) */
+			const int d = d0 + j, lo = max(-1, -1 - d), hi = min(tl - 1, ql - 1 - d);
+			if (hi >= lo) kmin[j] = lo, kspan[j] = hi - lo;
+			else kmin[j] = 0x3fffffff, kspan[j] = 0;
+		}
+		const int wd_lo = d0 - 4 * lane, wd_hi = wd_lo + 127;
+		const int bnd = (s0 | 0xff) + 1; /* next band trim */
+		int alive_bits = 0;
+		int hs = s0 % n, e1s = s0 % rm.d1, e2s = s0 % rm.d2;
+		mbar_wait(bar, phase);
+		phase ^= 1;
+		__syncthreads();
+		/* ---- Tb fused next+extend steps ---- */
+		for (int t = 1; t <= Tb; ++t) {
+			hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == rm.d1 ? 0 : e1s + 1, e2s = e2s + 1 == rm.d2 ? 0 : e2s + 1;
+			TileRows r; /* wf_next_prep, miniwfa.c:252-257 */
+			r.Hx = wrap_sub(hs, pen.x, n) * W, r.Ho1 = wrap_sub(hs, pen.oe1, n) * W, r.Ho2 = wrap_sub(hs, pen.oe2, n) * W;
+			const int pe1s = wrap_sub(e1s, pen.e1, rm.d1), pe2s = wrap_sub(e2s, pen.e2, rm.d2);
+			r.pE1 = (rm.bE1 + pe1s) * W, r.pF1 = (rm.bF1 + pe1s) * W, r.pE2 = (rm.bE2 + pe2s) * W, r.pF2 = (rm.bF2 + pe2s) * W;
+			r.nH = hs * W, r.nE1 = (rm.bE1 + e1s) * W, r.nF1 = (rm.bF1 + e1s) * W, r.nE2 = (rm.bE2 + e2s) * W, r.nF2 = (rm.bF2 + e2s) * W;
+			const int lo_t = left_edge ? max(wflo_c - 1, -tl) : -0x3fffffff;   /* :417-418 */
+			const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
+			const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
+			uint32_t tbw;
+			int4 nh, ve1, vf1, ve2, vf2;
+			int myfl;
+			if (edge) myfl = tile_cells<MODE, true>(rows, r, c, W, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, tid == 0, tid == NT - 1, useful, tbw, nh, ve1, vf1, ve2, vf2);
+			else myfl = tile_cells<MODE, false>(rows, r, c, W, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, tid == 0, tid == NT - 1, useful, tbw, nh, ve1, vf1, ve2, vf2);
+			if (MODE == MODE_TB && useful) __stcs(reinterpret_cast<uint32_t*>(P.arena + rowoff[t - 1] + (idx0 + c)), tbw);
+			if (s0 + t > bnd - n) { /* the slices wf_stripe_shrink will look at (:144-171) */
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const int d = d0 + j;
+					if (on_matrix_u(d, I4(nh, j), tl, ql) || on_matrix_u(d, I4(ve1, j), tl, ql) || on_matrix_u(d, I4(vf1, j), tl, ql) ||
+					    on_matrix_u(d, I4(ve2, j), tl, ql) || on_matrix_u(d, I4(vf2, j), tl, ql)) alive_bits |= 1 << j;
+				}
+			}
+			if (myfl) atomicOr(&sc[t % 3], myfl);
+			if (tid == 0) {
+				sc[(t + 1) % 3] = 0;
+				if (left_edge) ctl->lo_log[t - 1] = lo_t;
+				if (right_edge) ctl->hi_log[t - 1] = hi_t;
+			}
+			__syncthreads();
+			const int fl = sc[t % 3];
+			if (fl & FL_LO) wflo_c = lo_t;
+			if (fl & FL_HI) wfhi_c = hi_t;
+			if ((fl & FL_DONE) && tid == 0 && ctl->done_t == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
+		}
+		/* ---- store the useful columns of every row into the other state buffer ---- */
+		if (tid < 32) {
+			fence_async_smem();
+			for (int r = tid; r < R; r += 32)
+				bulk_s2g(st_out + (size_t)r * pitch + ustart, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
+			bulk_commit();
+		}
+		if (tid == 0) {
+			if (left_edge) ctl->fin_lo = wflo_c;
+			if (right_edge) ctl->fin_hi = wfhi_c;
+		}
+		if (s0 + Tb > bnd - n && useful) { /* alive words: tag = score of the coming trim | alive bit */
+			int4 *ap = reinterpret_cast<int4*>(P.alive + (size_t)slot * pitch + idx0 + c);
+			int4 a = *ap;
+			a.x = ((a.x & ~1) == bnd ? a.x : bnd) | (alive_bits & 1);
+			a.y = ((a.y & ~1) == bnd ? a.y : bnd) | (alive_bits >> 1 & 1);
+			a.z = ((a.z & ~1) == bnd ? a.z : bnd) | (alive_bits >> 2 & 1);
+			a.w = ((a.w & ~1) == bnd ? a.w : bnd) | (alive_bits >> 3 & 1);
+			*ap = a;
+		}
+		if (tid < 32) bulk_wait_read(); /* the rows may be overwritten by the next item's load */
+	}
+	if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* stores complete before the CTA retires */
+}
+
+/* wf_traceback (miniwfa.c:329-377) for the pairs of a wave: one warp per pair */
+__global__ void wfa_tile_traceback_kernel(const TParams P)
+{
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	const TileCtl *c = P.ctl + slot;
+	if (c->status != TS_DONE) return;
+	const PairDesc pd = P.pairs[pi];
+	Job J;
+	J.tl = pd.tl, J.ql = pd.ql, J.doff = tile_doff(P, pd.tl);
+	J.T8 = P.seq + pd.t_off, J.Q8 = P.seq + pd.q_off;
+	J.arena = P.arena;
+	J.rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
+	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap);
+	if (threadIdx.x == 0) {
+		P.outs[pi].n_cigar = n_cigar;
+		P.outs[pi].cigar_pos = pd.cigar_off + pd.cigar_cap - n_cigar;
+	}
+}
+
+#endif

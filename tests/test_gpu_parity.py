@@ -13,7 +13,7 @@ from oracle import orc
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [("cta", mw.KERNEL_CTA), ("grid", mw.KERNEL_GRID)]
+KERNELS = [("tile", mw.KERNEL_TILE), ("cta", mw.KERNEL_CTA), ("grid", mw.KERNEL_GRID)]
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -130,7 +130,7 @@ def random_opt(rng):
 def test_random_differential(kname, kernel):
     """Seeded random pairs and random valid penalty sets against the CPU checker."""
     mw.set_kernel(kernel)
-    rng = random.Random(42 if kname == "cta" else 43)
+    rng = random.Random({"cta": 42, "grid": 43}.get(kname, 44))
     for it in range(160):
         n = rng.choice([0, 1, 2, 5, 17, 60, 200, 300, 1000, 3000]) if it % 20 else 9000
         t = bytes(rng.choice(b"ACGT") for _ in range(n))
