@@ -23,7 +23,7 @@
  *   arena : traceback bytes, one row per score (bump-allocated, 1 byte per cell exactly as
  *           miniwfa.c:42) -- or, during low-memory pass 1, the snapshots.
  *   rowtab: int64 per score: arena offset of that score's row minus its first index.
- * Sequences: each padded to a 16-byte boundary with >=16 zero bytes of slack; match runs
+ * Sequences: each padded to a 16-byte boundary with >=64 zero bytes of slack; match runs
  * are clamped to the matrix, so no sentinel characters are required.
  *
  * No CPU fallback exists: every entry point aborts if no CUDA device is usable.
@@ -846,8 +846,8 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		if (tl[i] < 0 || ql[i] < 0) die("negative sequence length");
 		PairDesc &p = b->pairs[i];
 		p.tl = tl[i], p.ql = ql[i];
-		p.t_off = (long long)off; off += ((size_t)tl[i] + 16 + 15) & ~(size_t)15;
-		p.q_off = (long long)off; off += ((size_t)ql[i] + 16 + 15) & ~(size_t)15;
+		p.t_off = (long long)off; off += ((size_t)tl[i] + 64 + 15) & ~(size_t)15;
+		p.q_off = (long long)off; off += ((size_t)ql[i] + 64 + 15) & ~(size_t)15;
 		p.cigar_off = (long long)cw, p.cigar_cap = b->is_tb ? tl[i] + ql[i] + 2 : 0, p.pad_ = 0;
 		cw += (size_t)p.cigar_cap;
 		max_len = std::max(max_len, (long long)tl[i] + ql[i]);
@@ -858,7 +858,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	}
 	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
 		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
-	b->seq_bytes = off + 16, b->cigar_words = cw;
+	b->seq_bytes = off + 64, b->cigar_words = cw;
 
 	/* kernel family */
 	int pref = pick_kernel_pref();
@@ -869,9 +869,9 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	b->tNT = env_int("MWF_B200_TILE_THREADS", 256);
 	b->tW = 4 * b->tNT;
 	b->tR = n + 2 * (opt->e1 + 1) + 2 * (opt->e2 + 1);
-	b->tile_smem = (size_t)b->tR * b->tW * 4 + 64 + 8 * TILE_TMAX;
+	b->tile_smem = (size_t)b->tR * b->tW * 4 + 64;
 	const int umax = b->tW - 2 * b->tHL;
-	const bool tile_ok = !seg && n <= 64 && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 &&
+	const bool tile_ok = !seg && n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 &&
 		b->tile_smem <= (size_t)prop.sharedMemPerBlockOptin && umax / 2 - 4 >= 2 * b->tHL + n + 8;
 	if (pref == MWF_B200_KERNEL_TILE && !tile_ok) pref = MWF_B200_KERNEL_AUTO;
 	if (pref == MWF_B200_KERNEL_AUTO) {
@@ -1046,6 +1046,20 @@ static void run_tile(mwf_b200_batch_t *b)
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.seg = 0, P.seg_stride = 0;
+	{ /* row tables */
+		const int n = b->pen.nring, d1 = b->pen.e1 + 1, d2 = b->pen.e2 + 1, rb = b->tW * 4;
+		const int bE1 = n, bF1 = bE1 + d1, bE2 = bF1 + d1, bF2 = bE2 + d2;
+		for (int h = 0; h < n; ++h)
+			P.tabH[h] = make_int4(((h - b->pen.x + n) % n) * rb, ((h - b->pen.oe1 + n) % n) * rb, ((h - b->pen.oe2 + n) % n) * rb, h * rb);
+		for (int e = 0; e < d1; ++e) {
+			const int pe = (e - b->pen.e1 + d1) % d1;
+			P.tabE1[e] = make_int4((bE1 + pe) * rb, (bF1 + pe) * rb, (bE1 + e) * rb, (bF1 + e) * rb);
+		}
+		for (int e = 0; e < d2; ++e) {
+			const int pe = (e - b->pen.e2 + d2) % d2;
+			P.tabE2[e] = make_int4((bE2 + pe) * rb, (bF2 + pe) * rb, (bE2 + e) * rb, (bF2 + e) * rb);
+		}
+	}
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	for (int p0 = 0; p0 < b->n; p0 += b->wave_pairs) {
 		const int np = std::min(b->wave_pairs, b->n - p0);

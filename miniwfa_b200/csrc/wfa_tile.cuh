@@ -29,6 +29,8 @@
 #define WFA_TILE_CUH
 
 #define TILE_TMAX 64
+#define TILE_NRING_MAX 64
+#define TILE_EDEPTH_MAX 8
 
 enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4 };
 
@@ -38,6 +40,7 @@ struct TileCtl { /* per pair, lives in HBM for the whole run */
 	/* the block in flight */
 	int Tb, A4, total4, n_tiles;
 	int done_t, done_last, fin_lo, fin_hi;
+	long long row_base, row_size; /* traceback rows of the block: byte (row t, index i) at row_base + (t-1)*row_size + i */
 	int lo_log[TILE_TMAX], hi_log[TILE_TMAX];
 };
 
@@ -67,6 +70,10 @@ struct TParams {
 	long long rowtab_stride;
 	const int *seg;            /* pass-2 checkpoints (s,d) per pair, or null */
 	int seg_stride;
+	/* byte offsets of the rows a score touches inside a tile, by score modulo the ring depths (wf_next_prep, :252-257) */
+	int4 tabH[TILE_NRING_MAX];  /* [s % nring]  = {H[s-x], H[s-o1-e1], H[s-o2-e2], H[s]} */
+	int4 tabE1[TILE_EDEPTH_MAX]; /* [s % (e1+1)] = {E1[s-e1], F1[s-e1], E1[s], F1[s]} */
+	int4 tabE2[TILE_EDEPTH_MAX]; /* [s % (e2+1)] = {E2[s-e2], F2[s-e2], E2[s], F2[s]} */
 };
 
 __device__ __forceinline__ int tile_doff(const TParams &P, int tl) { return tl + P.pen.nring + P.HL + 8; }
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			else {
 				long long *rt = P.rowtab + (size_t)slot * P.rowtab_stride;
 				for (int t = 1; t <= Tb; ++t) rt[s + t] = (long long)base + (long long)(t - 1) * rowsize - A4;
+				c->row_base = (long long)base - A4, c->row_size = rowsize;
 			}
 		}
 		if (status == TS_RUN) {
@@ -258,31 +266,62 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 /* the tile kernel                                                                             */
 /* ------------------------------------------------------------------------------------------ */
 
-struct TileRows { /* shared-memory row bases (int32 index into the tile), for one score */
-	int Hx, Ho1, Ho2, pE1, pF1, pE2, pF2, nH, nE1, nF1, nE2, nF2;
-};
+/* shared-memory accesses with explicit 32-bit shared addresses (one add per row, no generic-address arithmetic) */
+__device__ __forceinline__ int4 lds4(uint32_t a)
+{
+	int4 v;
+	asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ int lds1(uint32_t a)
+{
+	int v;
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, int x, int y, int z, int w)
+{
+	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
-__device__ __forceinline__ int wrap_sub(int a, int b, int m) { int r = a - b; return r < 0 ? r + m : r; }
+/* 4 bytes of a sequence starting at byte `pos` (the funnel shift takes its amount modulo 32) */
+__device__ __forceinline__ uint32_t seq4(const uint32_t *__restrict__ w, int pos)
+{
+	const uint32_t *p = w + (pos >> 2);
+	return __funnelshift_r(__ldg(p), __ldg(p + 1), pos << 3);
+}
 
-/* one score step for the 4 diagonals of this thread.  EDGE = false: the whole warp lies strictly inside the
- * band and does not hold the terminal diagonal, so no masking, no edge rule, no termination test. */
+/* continue a match run: everything up to k is known to match (wf_extend1_padded, miniwfa.c:212-226), clamped to kmax */
+__device__ __noinline__ int tile_extend_more(const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q, int k, int d, int kmax)
+{
+	while (k < kmax) {
+		const uint32_t x = seq4(T, k + 1) ^ seq4(Q, d + k + 1);
+		if (x) { k += (__ffs(x) - 1) >> 3; break; }
+		k += 4;
+	}
+	return min(k, kmax);
+}
+
+/* one score step for the 4 diagonals of this thread; sb = shared address of the tile + 16 * tid.
+ * qh = {Hx, Ho1, Ho2, nH}, q1 = {pE1, pF1, nE1, nF1}, q2 = {pE2, pF2, nE2, nF2}: byte offsets of the rows (wf_next_prep, :252-257).
+ * EDGE = false: the whole warp lies strictly inside the band and does not hold the terminal diagonal,
+ * so no masking, no edge rule, no termination test. */
 template<int MODE, bool EDGE>
-__device__ __forceinline__ int tile_cells(int32_t *rows, const TileRows &r, int c, int W, int d0, int lo_t, int hi_t, int dfin, int tl,
-                                          const int (&kmin)[4], const int (&kspan)[4], const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
-                                          bool first_thread, bool last_thread, bool useful, uint32_t &tbw_out, int4 &newH,
-                                          int4 &vE1o, int4 &vF1o, int4 &vE2o, int4 &vF2o)
+__device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int4 &q1, const int4 &q2, int d0, int lo_t, int hi_t, int dfin, int tl,
+                                          const int (&kmin)[4], const int (&kspan)[4],
+                                          const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
+                                          bool no_left, bool no_right, bool useful, uint32_t &tbw_out,
+                                          int4 &oH, int4 &oE1, int4 &oF1, int4 &oE2, int4 &oF2)
 {
 	const int lane = threadIdx.x & 31;
-	const int4 ho1 = *reinterpret_cast<const int4*>(rows + r.Ho1 + c), pe1 = *reinterpret_cast<const int4*>(rows + r.pE1 + c);
-	const int4 pf1 = *reinterpret_cast<const int4*>(rows + r.pF1 + c), ho2 = *reinterpret_cast<const int4*>(rows + r.Ho2 + c);
-	const int4 pe2 = *reinterpret_cast<const int4*>(rows + r.pE2 + c), pf2 = *reinterpret_cast<const int4*>(rows + r.pF2 + c);
-	const int4 hx = *reinterpret_cast<const int4*>(rows + r.Hx + c);
+	const int4 ho1 = lds4(sb + qh.y), pe1 = lds4(sb + q1.x), pf1 = lds4(sb + q1.y), ho2 = lds4(sb + qh.z);
+	const int4 pe2 = lds4(sb + q2.x), pf2 = lds4(sb + q2.y), hx = lds4(sb + qh.x);
 	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		const int o1 = I4(ho1, j), o2 = I4(ho2, j), e1 = I4(pe1, j), e2 = I4(pe2, j), f1 = I4(pf1, j), f2 = I4(pf2, j);
 		A1[j + 1] = max(o1, e1), A2[j + 1] = max(o2, e2);
-		C1[j + 1] = max(o1, f1) + 1, C2[j + 1] = max(o2, f2) + 1;
+		C1[j + 1] = max(o1, f1), C2[j + 1] = max(o2, f2); /* the +1 of F is applied below */
 		if (MODE != MODE_SCORE) bA1[j + 1] = o1 < e1, bA2[j + 1] = o2 < e2, bC1[j + 1] = o1 < f1, bC2[j + 1] = o2 < f2;
 	}
 	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
@@ -294,25 +333,30 @@ __device__ __forceinline__ int tile_cells(int32_t *rows, const TileRows &r, int 
 		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
 		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
 	}
-	if (lane == 0) { /* left neighbour belongs to another warp (or to nobody: stale halo) */
-		int o1 = NEG_INF, e1 = NEG_INF, o2 = NEG_INF, e2 = NEG_INF;
-		if (!first_thread) o1 = rows[r.Ho1 + c - 1], e1 = rows[r.pE1 + c - 1], o2 = rows[r.Ho2 + c - 1], e2 = rows[r.pE2 + c - 1];
-		A1[0] = max(o1, e1), A2[0] = max(o2, e2);
-		if (MODE != MODE_SCORE) bA1[0] = o1 < e1, bA2[0] = o2 < e2;
+	if (lane == 0 || lane == 31) { /* the neighbour belongs to another warp (or to nobody: stale halo) */
+		const bool left = lane == 0;
+		const uint32_t nb = sb + (left ? -4 : 16);
+		int o1 = NEG_INF, x1 = NEG_INF, o2 = NEG_INF, x2 = NEG_INF;
+		if (!(left ? no_left : no_right)) {
+			o1 = lds1(nb + qh.y), o2 = lds1(nb + qh.z);
+			x1 = lds1(nb + (left ? q1.x : q1.y)), x2 = lds1(nb + (left ? q2.x : q2.y));
+		}
+		const int m1 = max(o1, x1), m2 = max(o2, x2);
+		if (left) {
+			A1[0] = m1, A2[0] = m2;
+			if (MODE != MODE_SCORE) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
+		} else {
+			C1[5] = m1, C2[5] = m2;
+			if (MODE != MODE_SCORE) bC1[5] = o1 < x1, bC2[5] = o2 < x2;
+		}
 	}
-	if (lane == 31) {
-		int o1 = NEG_INF, f1 = NEG_INF, o2 = NEG_INF, f2 = NEG_INF;
-		if (!last_thread) o1 = rows[r.Ho1 + c + 4], f1 = rows[r.pF1 + c + 4], o2 = rows[r.Ho2 + c + 4], f2 = rows[r.pF2 + c + 4];
-		C1[5] = max(o1, f1) + 1, C2[5] = max(o2, f2) + 1;
-		if (MODE != MODE_SCORE) bC1[5] = o1 < f1, bC2[5] = o2 < f2;
-	}
-	int vH[4], vE1[4], vF1[4], vE2[4], vF2[4], st[4];
+	int vH[4], vE1[4], vF1[4], vE2[4], vF2[4], st[4] = {0, 0, 0, 0}, h0[4];
 	bool ext[4];
 	uint32_t tbw = 0;
 	int myfl = 0;
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
-		int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2], F2 = C2[j + 2];
+		int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2] + 1, F2 = C2[j + 2] + 1;
 		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = I4(hx, j) + 1;
 		int H = max(hxp, gmx);
 		if (MODE != MODE_SCORE) { /* the 7-bit pack, miniwfa.c:290-306 */
@@ -328,37 +372,49 @@ __device__ __forceinline__ int tile_cells(int32_t *rows, const TileRows &r, int 
 				if (d == hi_t) myfl |= FL_HI;
 			}
 		}
-		vE1[j] = E1, vE2[j] = E2, vF1[j] = F1, vF2[j] = F2, vH[j] = H;
+		vE1[j] = E1, vE2[j] = E2, vF1[j] = F1, vF2[j] = F2, h0[j] = H;
 		ext[j] = (unsigned)(H - kmin[j]) <= (unsigned)kspan[j]; /* on the matrix (:402) */
 	}
+	/* wf_extend (:400-411): first probe of the match run, 4 bytes per sequence, all loads in flight together */
 	uint32_t px[4];
 #pragma unroll
-	for (int j = 0; j < 4; ++j) { /* first probe of the match run, all four loads in flight together */
-		const int tp = ext[j] ? vH[j] + 1 : 0, qp = ext[j] ? d0 + j + vH[j] + 1 : 0;
-		px[j] = seq_word(T, tp) ^ seq_word(Q, qp);
+	for (int j = 0; j < 4; ++j) {
+		const int tp = ext[j] ? h0[j] + 1 : 0, qp = ext[j] ? d0 + j + h0[j] + 1 : 0;
+		px[j] = seq4(T, tp) ^ seq4(Q, qp);
 	}
+	oE1 = make_int4(vE1[0], vE1[1], vE1[2], vE1[3]), oF1 = make_int4(vF1[0], vF1[1], vF1[2], vF1[3]);
+	oE2 = make_int4(vE2[0], vE2[1], vE2[2], vE2[3]), oF2 = make_int4(vF2[0], vF2[1], vF2[2], vF2[3]);
+	sts4(sb + q1.z, vE1[0], vE1[1], vE1[2], vE1[3]);
+	sts4(sb + q1.w, vF1[0], vF1[1], vF1[2], vF1[3]);
+	sts4(sb + q2.z, vE2[0], vE2[1], vE2[2], vE2[3]);
+	sts4(sb + q2.w, vF2[0], vF2[1], vF2[2], vF2[3]);
+	bool more = false;
+	bool unres[4];
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
-		if (!ext[j]) continue;
-		const int h0 = vH[j], kmax = kmin[j] + kspan[j];
-		int k;
-		if (px[j]) k = min(h0 + ((__ffs(px[j]) - 1) >> 3), kmax);
-		else k = extend_run(T, Q, min(h0 + 4, kmax), d0 + j, kmax);
-		if (EDGE && useful && d0 + j == dfin && k == tl - 1) { /* end of both sequences, :405-409 */
-			myfl |= FL_DONE;
-			if (MODE == MODE_TB && k == h0) myfl |= st[j] << FL_LAST_SHIFT;
-		}
-		vH[j] = k;
+		const int kmax = kmin[j] + kspan[j];
+		const int adv = px[j] ? (__ffs(px[j]) - 1) >> 3 : 4;
+		const int k = min(h0[j] + adv, kmax);
+		unres[j] = ext[j] && px[j] == 0 && k < kmax;
+		more |= unres[j];
+		vH[j] = ext[j] ? k : h0[j];
 	}
-	*reinterpret_cast<int4*>(rows + r.nH + c) = make_int4(vH[0], vH[1], vH[2], vH[3]);
-	*reinterpret_cast<int4*>(rows + r.nE1 + c) = make_int4(vE1[0], vE1[1], vE1[2], vE1[3]);
-	*reinterpret_cast<int4*>(rows + r.nF1 + c) = make_int4(vF1[0], vF1[1], vF1[2], vF1[3]);
-	*reinterpret_cast<int4*>(rows + r.nE2 + c) = make_int4(vE2[0], vE2[1], vE2[2], vE2[3]);
-	*reinterpret_cast<int4*>(rows + r.nF2 + c) = make_int4(vF2[0], vF2[1], vF2[2], vF2[3]);
+	if (more) { /* rare: a run longer than the first probe */
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (unres[j]) vH[j] = tile_extend_more(T, Q, vH[j], d0 + j, kmin[j] + kspan[j]);
+	}
+	if (EDGE && useful && dfin >= d0 && dfin < d0 + 4) { /* end of both sequences, :405-409 */
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (d0 + j == dfin && ext[j] && vH[j] == tl - 1) {
+				myfl |= FL_DONE;
+				if (MODE == MODE_TB && vH[j] == h0[j]) myfl |= st[j] << FL_LAST_SHIFT;
+			}
+	}
+	oH = make_int4(vH[0], vH[1], vH[2], vH[3]);
+	sts4(sb + qh.w, vH[0], vH[1], vH[2], vH[3]);
 	tbw_out = tbw;
-	newH = make_int4(vH[0], vH[1], vH[2], vH[3]);
-	vE1o = make_int4(vE1[0], vE1[1], vE1[2], vE1[3]), vF1o = make_int4(vF1[0], vF1[1], vF1[2], vF1[3]);
-	vE2o = make_int4(vE2[0], vE2[1], vE2[2], vE2[3]), vF2o = make_int4(vF2[0], vF2[1], vF2[2], vF2[3]);
 	return myfl;
 }
 
@@ -367,21 +423,32 @@ __device__ __forceinline__ bool on_matrix_u(int d, int k, int tl, int ql)
 	return (unsigned)(k + 1) <= (unsigned)tl && (unsigned)(d + k + 1) <= (unsigned)ql;
 }
 
-/* shared memory: rows[R][W] int32 | ctl ints [16] | mbarrier | rowoff[TILE_TMAX] */
+__device__ __forceinline__ int alive4(int d0, int tl, int ql, const int4 &nh, const int4 &ve1, const int4 &vf1, const int4 &ve2, const int4 &vf2)
+{
+	int bits = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int d = d0 + j;
+		if (on_matrix_u(d, I4(nh, j), tl, ql) || on_matrix_u(d, I4(ve1, j), tl, ql) || on_matrix_u(d, I4(vf1, j), tl, ql) ||
+		    on_matrix_u(d, I4(ve2, j), tl, ql) || on_matrix_u(d, I4(vf2, j), tl, ql)) bits |= 1 << j;
+	}
+	return bits;
+}
+
+/* shared memory: rows[R][W] int32 | ctl ints [16] (flags, item, mbarrier) */
 template<int MODE>
-__global__ void __launch_bounds__(512) wfa_tile_kernel(const TParams P, int it)
+__global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ TParams P, int it)
 {
 	extern __shared__ __align__(128) int32_t smem_tile[];
 	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
 	int32_t *rows = smem_tile;
 	int *sc = rows + (size_t)R * W;                          /* [0..2] flags, [3] item */
 	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8);
-	long long *rowoff = reinterpret_cast<long long*>(sc + 16);
 	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
-	const Pen pen = P.pen;
-	const RowMap rm(pen);
-	const int n = pen.nring;
+	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
 	const unsigned int n_items = P.cnt[it & 1].n_items;
+	const uint32_t sb = smem_u32(rows) + 16 * tid;
+	const bool no_left = tid == 0, no_right = tid == NT - 1;
 	if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 	uint32_t phase = 0;
 	for (;;) {
@@ -411,11 +478,14 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const TParams P, int it)
 			for (int r = tid; r < R; r += 32)
 				bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
 		}
-		if (MODE == MODE_TB && tid < Tb) rowoff[tid] = P.rowtab[(size_t)slot * P.rowtab_stride + s0 + 1 + tid];
 		if (tid < 3) sc[tid] = 0;
 		const uint32_t *T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), *Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off);
 		const int c = 4 * tid, d0 = idx0 + c - doff;
 		const bool useful = c >= HL && c < HL + ulen;
+		const bool special = left_edge || right_edge || (dfin >= idx0 - doff && dfin < idx0 - doff + W); /* flags matter */
+		uint8_t *tbp = 0; /* traceback byte of this thread's first diagonal at the block's first score (wf_tb_add, :33-44) */
+		long long tb_pitch = 0;
+		if (MODE == MODE_TB) tbp = P.arena + ctl->row_base + (idx0 + c), tb_pitch = ctl->row_size;
 		int kmin[4], kspan[4];
 #pragma unroll
 		for (int j = 0; j < 4; ++j) { /* H is on the matrix iff kmin <= H <= kmin + kspan (:402) */
@@ -425,47 +495,48 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const TParams P, int it)
 		}
 		const int wd_lo = d0 - 4 * lane, wd_hi = wd_lo + 127;
 		const int bnd = (s0 | 0xff) + 1; /* next band trim */
+		const int t_alive = bnd - n - s0; /* steps t > t_alive feed wf_stripe_shrink (:144-171) */
 		int alive_bits = 0;
-		int hs = s0 % n, e1s = s0 % rm.d1, e2s = s0 % rm.d2;
+		int hs = s0 % n, e1s = s0 % d1, e2s = s0 % d2;
 		mbar_wait(bar, phase);
 		phase ^= 1;
 		__syncthreads();
 		/* ---- Tb fused next+extend steps ---- */
-		for (int t = 1; t <= Tb; ++t) {
-			hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == rm.d1 ? 0 : e1s + 1, e2s = e2s + 1 == rm.d2 ? 0 : e2s + 1;
-			TileRows r; /* wf_next_prep, miniwfa.c:252-257 */
-			r.Hx = wrap_sub(hs, pen.x, n) * W, r.Ho1 = wrap_sub(hs, pen.oe1, n) * W, r.Ho2 = wrap_sub(hs, pen.oe2, n) * W;
-			const int pe1s = wrap_sub(e1s, pen.e1, rm.d1), pe2s = wrap_sub(e2s, pen.e2, rm.d2);
-			r.pE1 = (rm.bE1 + pe1s) * W, r.pF1 = (rm.bF1 + pe1s) * W, r.pE2 = (rm.bE2 + pe2s) * W, r.pF2 = (rm.bF2 + pe2s) * W;
-			r.nH = hs * W, r.nE1 = (rm.bE1 + e1s) * W, r.nF1 = (rm.bF1 + e1s) * W, r.nE2 = (rm.bE2 + e2s) * W, r.nF2 = (rm.bF2 + e2s) * W;
-			const int lo_t = left_edge ? max(wflo_c - 1, -tl) : -0x3fffffff;   /* :417-418 */
-			const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
-			const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
-			uint32_t tbw;
-			int4 nh, ve1, vf1, ve2, vf2;
-			int myfl;
-			if (edge) myfl = tile_cells<MODE, true>(rows, r, c, W, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, tid == 0, tid == NT - 1, useful, tbw, nh, ve1, vf1, ve2, vf2);
-			else myfl = tile_cells<MODE, false>(rows, r, c, W, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, tid == 0, tid == NT - 1, useful, tbw, nh, ve1, vf1, ve2, vf2);
-			if (MODE == MODE_TB && useful) __stcs(reinterpret_cast<uint32_t*>(P.arena + rowoff[t - 1] + (idx0 + c)), tbw);
-			if (s0 + t > bnd - n) { /* the slices wf_stripe_shrink will look at (:144-171) */
-#pragma unroll
-				for (int j = 0; j < 4; ++j) {
-					const int d = d0 + j;
-					if (on_matrix_u(d, I4(nh, j), tl, ql) || on_matrix_u(d, I4(ve1, j), tl, ql) || on_matrix_u(d, I4(vf1, j), tl, ql) ||
-					    on_matrix_u(d, I4(ve2, j), tl, ql) || on_matrix_u(d, I4(vf2, j), tl, ql)) alive_bits |= 1 << j;
+		uint32_t tbw;
+		int4 nh, ve1, vf1, ve2, vf2;
+		if (!special) {
+			for (int t = 1; t <= Tb; ++t) {
+				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
+				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
+				tile_cells<MODE, false>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
+				if (MODE == MODE_TB) { if (useful) __stcs(reinterpret_cast<uint32_t*>(tbp), tbw); tbp += tb_pitch; }
+				if (t > t_alive) alive_bits |= alive4(d0, tl, ql, nh, ve1, vf1, ve2, vf2);
+				__syncthreads();
+			}
+		} else {
+			for (int t = 1; t <= Tb; ++t) {
+				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
+				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
+				const int lo_t = left_edge ? max(wflo_c - 1, -tl) : -0x3fffffff;   /* :417-418 */
+				const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
+				const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
+				if (edge) {
+					const int myfl = tile_cells<MODE, true>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
+					if (myfl) atomicOr(&sc[t % 3], myfl);
+				} else tile_cells<MODE, false>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
+				if (MODE == MODE_TB) { if (useful) __stcs(reinterpret_cast<uint32_t*>(tbp), tbw); tbp += tb_pitch; }
+				if (t > t_alive) alive_bits |= alive4(d0, tl, ql, nh, ve1, vf1, ve2, vf2);
+				if (tid == 0) {
+					sc[(t + 1) % 3] = 0;
+					if (left_edge) ctl->lo_log[t - 1] = lo_t;
+					if (right_edge) ctl->hi_log[t - 1] = hi_t;
 				}
+				__syncthreads();
+				const int fl = sc[t % 3];
+				if (fl & FL_LO) wflo_c = lo_t;
+				if (fl & FL_HI) wfhi_c = hi_t;
+				if ((fl & FL_DONE) && tid == 0 && ctl->done_t == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
 			}
-			if (myfl) atomicOr(&sc[t % 3], myfl);
-			if (tid == 0) {
-				sc[(t + 1) % 3] = 0;
-				if (left_edge) ctl->lo_log[t - 1] = lo_t;
-				if (right_edge) ctl->hi_log[t - 1] = hi_t;
-			}
-			__syncthreads();
-			const int fl = sc[t % 3];
-			if (fl & FL_LO) wflo_c = lo_t;
-			if (fl & FL_HI) wfhi_c = hi_t;
-			if ((fl & FL_DONE) && tid == 0 && ctl->done_t == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
 		}
 		/* ---- store the useful columns of every row into the other state buffer ---- */
 		if (tid < 32) {
@@ -478,7 +549,7 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const TParams P, int it)
 			if (left_edge) ctl->fin_lo = wflo_c;
 			if (right_edge) ctl->fin_hi = wfhi_c;
 		}
-		if (s0 + Tb > bnd - n && useful) { /* alive words: tag = score of the coming trim | alive bit */
+		if (Tb > t_alive && useful) { /* alive words: tag = score of the coming trim | alive bit */
 			int4 *ap = reinterpret_cast<int4*>(P.alive + (size_t)slot * pitch + idx0 + c);
 			int4 a = *ap;
 			a.x = ((a.x & ~1) == bnd ? a.x : bnd) | (alive_bits & 1);
