@@ -9,6 +9,7 @@ changes (weak scaling).  One "step" = one pass of the hot path over this rank's 
   e2e   : the same through the C-ABI call a user makes (mwf_wfa_exact_batch semantics: create, stage host buffers
           through pinned memory, H2D, kernels, D2H of the results), host wall clock around the call
   roofline     : wavefront cells (r.n_iter) x 64 algorithmic bytes / kernel time, against the measured HBM copy peak
+                 (the tile engine keeps the ring in shared memory: `traffic` = measured DRAM bytes per pass, from ncu)
   cpu_baseline : the unmodified reference (oracle/_ref) or the oracle port timed on this box's host cores
   single_pair  : BASELINE.json config 2 surrogate (one 150 kb pair, CIGAR, high-memory) on one GPU, for reference
 
@@ -188,7 +189,8 @@ def workload_config(args, world):
                         % (args.pairs_per_gpu * world, args.len, args.div * 100, args.pairs_per_gpu),
             "pairs_per_gpu": args.pairs_per_gpu, "pairs_total": args.pairs_per_gpu * world, "seq_len": args.len,
             "divergence": args.div, "mode": "score-only", "parallelism": "pairs sharded across GPUs, no data-path collective",
-            "l2": "no flush: the wavefront ring working set (~1 GB per GPU) and the per-step traffic are far larger than the 126 MB L2"}
+            "l2": "no flush: the wavefront state a pass streams through (2 x 27 rows x ~50k diagonals x 4 B x 128 pairs ~ 1.4 GB per "
+                  "time block, 5.5 GB allocated) is far larger than the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -261,7 +263,7 @@ def main():
     ev0.record(stream)
     for _ in range(args.steps):
         b.run()
-        launches += 1  # one persistent kernel per pass (counted again from the engine below)
+        launches += 1  # counted again from the engine below
     ev1.record(stream)
     b.wait()
     torch.cuda.synchronize()
@@ -269,9 +271,11 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
-    launches = int(b.launches) * args.steps
+    b_launches = int(b.launches)
+    launches = b_launches * args.steps
     res = b.fetch()
-    kernel_used = {mw.KERNEL_CTA: "cta", mw.KERNEL_GRID: "grid"}.get(b.kernel_used, "?")
+    fam_names = {mw.KERNEL_CTA: "cta", mw.KERNEL_GRID: "grid", mw.KERNEL_TILE: "tile"}
+    kernel_used = fam_names.get(b.kernel_used, "?")
     # per-launch kernel duration, measured live by the engine's own CUDA events around the kernel of the last pass
     b.run()
     b.wait()
@@ -320,10 +324,16 @@ def main():
             traffic = json.load(open(tp)).get("bench_kernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    per_pass = int(b_launches)
     roofline = {"bound": "hbm", "kernel": "wfa_%s_kernel" % kernel_used, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": BYTES_PER_CELL_SCORE, "cells_per_launch": ni_local,
-                "kernel_ms": kernel_ms[0], "kernel_ms_max_over_ranks": k_ms}
+                "algorithmic_bytes_per_cell": BYTES_PER_CELL_SCORE, "cells_per_pass": ni_local,
+                "launches_per_pass": per_pass,
+                "kernel_ms": kernel_ms[0], "kernel_ms_max_over_ranks": k_ms,
+                "note": "one pass over the batch = launches_per_pass launches (score-0 init, then one plan + one tile kernel per block "
+                        "of 64 scores); kernel_ms is the CUDA-event time over all of them on the launching stream, so achieved = "
+                        "cells_per_pass x 64 B / kernel_ms understates the tile kernel alone; the tile engine keeps the ring in shared "
+                        "memory, so its DRAM traffic (`traffic`, per pass, from ncu) is far below the algorithmic bytes"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -342,17 +352,19 @@ def main():
                 sb.wait()
             r1 = sb.fetch()[0]
             kms = sb.kernel_ms
-            fam = {mw.KERNEL_CTA: "cta", mw.KERNEL_GRID: "grid"}.get(sb.kernel_used, "?")
+            fam = fam_names.get(sb.kernel_used, "?")
+            launches1 = int(sb.launches)
         t0 = time.perf_counter()
         r2 = mw.wfa_exact(o2, t, q)
         e2e1 = time.perf_counter() - t0
         assert r2 == r1 and mw.cigar2score(o2, r1[3]) == (r1[0], len(t), len(q))
         n1 = max(len(t), len(q))
         line["single_pair"] = {"workload": "BASELINE config 2 surrogate: one synthetic 150 kb pair (p=0.038), CIGAR, high-memory",
-                               "s": r1[0], "n_iter": r1[2], "n_cigar": r1[1], "kernel": fam, "kernel_ms": kms,
+                               "s": r1[0], "n_iter": r1[2], "n_cigar": r1[1], "kernel": fam, "kernel_ms": kms, "gpu_launches": launches1,
                                "value": n1 * r1[0] / (kms * 1e-3), "e2e_value": n1 * r1[0] / e2e1, "unit": UNIT,
                                "roofline_frac": r1[2] * BYTES_PER_CELL_TB / (kms * 1e-3) / 1e9 / peak,
-                               "note": "one pair = one dependency chain of s grid-wide barriers: latency-bound, not HBM-bound"}
+                               "note": "one pair = one dependency chain of s scores; the tile engine cuts it into blocks of 64 scores "
+                                       "x (width/896) tiles, so only ~30-60 of the 148 SMs have work: latency-bound, not HBM-bound"}
 
     # ---- cpu_baseline: rank 0 at N=1 only ---------------------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
