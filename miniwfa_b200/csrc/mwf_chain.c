@@ -1,10 +1,293 @@
-/* placeholder replaced below in this round: see mwf_chain.c */
-#include <stdio.h>
+/*
+ * mwf_chain.c -- mwf_wfa_chain(): the k-mer chaining heuristic of the reference (miniwfa.c:620-896), host C.
+ *
+ * Same result as the reference (same anchors, same score, same CIGAR words): unique k-mer matches (k = opt->kmer,
+ * at most opt->max_occ copies per sequence, :718-767) -> longest strictly increasing chain (:678-697, :769-783) ->
+ * co-diagonal runs shorter than opt->min_len dropped (:829-848) -> the gaps between anchors filled (:861-891).
+ *
+ * What is different is *how* the gaps are filled.  The reference calls mwf_wfa_exact() once per gap, one after the
+ * other (:877).  Here every gap that needs an exact alignment is collected first and the whole set goes to the GPU
+ * engine as ONE batch (mwf_wfa_exact_batch, mwf_b200.h): many small independent alignments are exactly what the
+ * engine is built for.  The gaps are independent, so the per-gap results -- and therefore the
+ * concatenated CIGAR and the summed score -- are the same.
+ *
+ * Like the reference, this function does not touch r->n_iter (:850-896 never writes it).
+ */
+#include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
+#include <assert.h>
 #include "miniwfa.h"
+#include "mwf_b200.h"
+#include "kalloc.h"
+
+/* ---- CIGAR assembly (reference :46-62, :816-827) ---- */
+
+typedef struct { uint32_t *w; int32_t n, cap; } cigbuf_t;
+
+static void cig_reserve(void *km, cigbuf_t *c, int32_t extra)
+{
+	if (c->n + extra > c->cap) {
+		int32_t cap = c->cap + (c->cap >> 1) + 4;
+		if (cap < c->n + extra) cap = c->n + extra;
+		c->w = (uint32_t*)krealloc(km, c->w, sizeof(uint32_t) * (size_t)cap);
+		c->cap = cap;
+	}
+}
+
+static void cig_add(void *km, cigbuf_t *c, int op, int32_t len) /* an operation equal to the last one is merged into it */
+{
+	if (c->n > 0 && (int)(c->w[c->n - 1] & 0xf) == op) c->w[c->n - 1] += (uint32_t)len << 4;
+	else {
+		cig_reserve(km, c, 1);
+		c->w[c->n++] = (uint32_t)len << 4 | (uint32_t)op;
+	}
+}
+
+static void cig_cat(void *km, cigbuf_t *c, int32_t n, const uint32_t *w) /* only the first word can merge */
+{
+	if (n <= 0) return;
+	cig_add(km, c, (int)(w[0] & 0xf), (int32_t)(w[0] >> 4));
+	cig_reserve(km, c, n - 1);
+	memcpy(c->w + c->n, w + 1, sizeof(uint32_t) * (size_t)(n - 1));
+	c->n += n - 1;
+}
+
+/* ---- k-mers (reference :699-730) ---- */
+
+static inline int base_code(unsigned char ch) /* A/C/G/T(U) in either case, or the raw codes 0..3; anything else breaks a k-mer */
+{
+	switch (ch) {
+	case 0: case 'A': case 'a': return 0;
+	case 1: case 'C': case 'c': return 1;
+	case 2: case 'G': case 'g': return 2;
+	case 3: case 'T': case 't': case 'U': case 'u': return 3;
+	default: return 4;
+	}
+}
+
+/* every k-mer of seq as (k-mer << 1 | which) << 32 | position of its last base */
+static int32_t list_kmers(int32_t len, const char *seq, int which, int k, uint64_t *out)
+{
+	const uint64_t mask = (1ULL << 2 * k) - 1;
+	uint64_t word = 0;
+	int32_t i, run = 0, n = 0;
+	for (i = 0; i < len; ++i) {
+		const int c = base_code((unsigned char)seq[i]);
+		if (c > 3) { run = 0, word = 0; continue; }
+		word = (word << 2 | (uint64_t)c) & mask;
+		if (++run >= k) out[n++] = (word << 1 | (uint64_t)which) << 32 | (uint32_t)i;
+	}
+	return n;
+}
+
+/* ascending sort of distinct 64-bit keys: byte-wise LSD radix sort, passes whose byte is constant are skipped */
+static void sort64(void *km, uint64_t *a, size_t n)
+{
+	uint64_t *tmp, *src = a, *dst;
+	int pass;
+	if (n < 2) return;
+	tmp = (uint64_t*)kmalloc(km, sizeof(uint64_t) * n);
+	dst = tmp;
+	for (pass = 0; pass < 8; ++pass) {
+		size_t cnt[256], i, sum = 0;
+		const int sh = pass * 8;
+		memset(cnt, 0, sizeof(cnt));
+		for (i = 0; i < n; ++i) ++cnt[src[i] >> sh & 0xff];
+		if (cnt[src[0] >> sh & 0xff] == n) continue;
+		for (i = 0; i < 256; ++i) { const size_t c = cnt[i]; cnt[i] = sum; sum += c; }
+		for (i = 0; i < n; ++i) dst[cnt[src[i] >> sh & 0xff]++] = src[i];
+		{ uint64_t *t = src; src = dst; dst = t; }
+	}
+	if (src != a) memcpy(a, src, sizeof(uint64_t) * n);
+	kfree(km, tmp);
+}
+
+/* longest strictly increasing subsequence of v[0..n); writes the chosen indices to pick[], returns their number (:678-697) */
+static int32_t longest_increasing(void *km, int32_t n, const uint64_t *v, int32_t *pick)
+{
+	int32_t *tail, *prev, i, len = 0, at;
+	if (n <= 0) return 0;
+	tail = (int32_t*)kmalloc(km, sizeof(int32_t) * ((size_t)n + 1)); /* tail[l] = index ending the best chain of length l */
+	prev = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)n);
+	for (i = 0; i < n; ++i) {
+		int32_t lo = 0, hi = len; /* number of tails strictly below v[i] */
+		while (lo < hi) {
+			const int32_t mid = (lo + hi + 1) >> 1;
+			if (v[tail[mid]] < v[i]) lo = mid; else hi = mid - 1;
+		}
+		prev[i] = lo > 0 ? tail[lo] : -1;
+		tail[lo + 1] = i;
+		if (lo + 1 > len) len = lo + 1;
+	}
+	for (i = len - 1, at = tail[len]; i >= 0; --i) pick[i] = at, at = prev[at];
+	kfree(km, prev);
+	kfree(km, tail);
+	return len;
+}
+
+/* anchors (target position << 32 | query position, last base of the k-mer) of the best co-linear chain (:732-784) */
+static uint64_t *chain_anchors(void *km, int32_t tl, const char *ts, int32_t ql, const char *qs, int k, int max_occ, int32_t *n_out)
+{
+	uint64_t *km_list, *hit = 0, *anchors;
+	int32_t n_km, n_hit = 0, cap_hit = 0, i, g0, *pick, n_pick;
+	*n_out = 0;
+	if (tl < k || ql < k) return 0;
+	assert(k >= 2 && k <= 15);
+	km_list = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)tl + ql));
+	n_km = list_kmers(tl, ts, 0, k, km_list);
+	n_km += list_kmers(ql, qs, 1, k, km_list + n_km);
+	sort64(km, km_list, (size_t)n_km);
+	for (g0 = 0, i = 1; i <= n_km; ++i) { /* groups of equal k-mers; inside a group the target copies come first */
+		int32_t split, s, t;
+		if (i < n_km && km_list[i] >> 33 == km_list[g0] >> 33) continue;
+		for (split = g0; split < i && (km_list[split] >> 32 & 1) == 0; ++split) {}
+		if (split > g0 && split < i && split - g0 <= max_occ && i - split <= max_occ)
+			for (s = g0; s < split; ++s)
+				for (t = split; t < i; ++t) {
+					if (n_hit == cap_hit) {
+						cap_hit = cap_hit ? cap_hit + (cap_hit >> 1) : 256;
+						hit = (uint64_t*)krealloc(km, hit, sizeof(uint64_t) * (size_t)cap_hit);
+					}
+					hit[n_hit++] = km_list[s] << 32 | (uint32_t)km_list[t];
+				}
+		g0 = i;
+	}
+	kfree(km, km_list);
+	sort64(km, hit, (size_t)n_hit); /* by target position, then query position */
+	for (i = 0; i < n_hit; ++i) hit[i] = hit[i] >> 32 | hit[i] << 32; /* compare on (query, target) */
+	pick = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)(n_hit > 0 ? n_hit : 1));
+	n_pick = longest_increasing(km, n_hit, hit, pick);
+	anchors = (uint64_t*)kmalloc(km, sizeof(uint64_t) * (size_t)(n_pick > 0 ? n_pick : 1));
+	for (i = 0; i < n_pick; ++i) anchors[i] = hit[pick[i]] >> 32 | hit[pick[i]] << 32;
+	kfree(km, pick);
+	kfree(km, hit);
+	*n_out = n_pick;
+	return anchors;
+}
+
+/* drop runs of co-diagonal anchors that span fewer than min_len bases (:829-848) */
+static int32_t drop_short_runs(int32_t n, uint64_t *a, int32_t tl, int32_t ql, int k, int32_t min_len)
+{
+	int32_t i, j, m, run_start = -1, run_len = 0, ox = 0, oy = 0, px = 0;
+	for (i = 0; i <= n; ++i) {
+		const int32_t x = i == n ? tl : (int32_t)(a[i] >> 32) + 1, y = i == n ? ql : (int32_t)(uint32_t)a[i] + 1;
+		if (x - ox != y - oy) { /* leaves the diagonal of the run's first anchor */
+			if (run_len < min_len)
+				for (j = run_start > 0 ? run_start : 0; j < i; ++j) a[j] = 0;
+			ox = x, oy = y, run_start = i, run_len = k;
+		} else run_len += x - px;
+		px = x;
+	}
+	for (i = m = 0; i < n; ++i)
+		if (a[i] != 0) a[m++] = a[i];
+	return m;
+}
+
+/* fraction of shared k-mers, the larger of the two directions (:786-812) */
+static double kmer_similarity(void *km, int32_t l1, const char *s1, int32_t l2, const char *s2, int k)
+{
+	uint64_t *a;
+	int32_t n, i, g0, n1 = 0, n2 = 0, t1 = 0, t2 = 0;
+	double p1, p2;
+	if (l1 < k || l2 < k) return 0;
+	a = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)l1 + l2));
+	n = list_kmers(l1, s1, 0, k, a);
+	n += list_kmers(l2, s2, 1, k, a + n);
+	sort64(km, a, (size_t)n);
+	for (g0 = 0, i = 1; i <= n; ++i) {
+		int32_t split, c1, c2, shared;
+		if (i < n && a[i] >> 33 == a[g0] >> 33) continue;
+		for (split = g0; split < i && (a[split] >> 32 & 1) == 0; ++split) {}
+		c1 = split - g0, c2 = i - split, shared = c1 < c2 ? c1 : c2;
+		n1 += c1, n2 += c2;
+		if (c1 > 0 && c2 > 0) t1 += shared, t2 += shared;
+		g0 = i;
+	}
+	kfree(km, a);
+	p1 = (double)t1 / n1, p2 = (double)t2 / n2;
+	return p1 > p2 ? p1 : p2;
+}
+
+static int32_t one_gap_cost(const mwf_opt_t *opt, int32_t len)
+{
+	const int32_t a = opt->o2 + len * opt->e2, b = opt->o1 + len * opt->e1;
+	return a < b ? a : b;
+}
+
+enum { SEG_MATCH, SEG_TWO_GAPS, SEG_EXACT, SEG_DEL, SEG_INS, SEG_NONE };
+
+typedef struct { int32_t kind, x0, y0, x1, y1, job; } seg_t;
+
 void mwf_wfa_chain(void *km, const mwf_opt_t *opt, int32_t tl, const char *ts, int32_t ql, const char *qs, mwf_rst_t *r)
 {
-	(void)km; (void)opt; (void)tl; (void)ts; (void)ql; (void)qs; (void)r;
-	fprintf(stderr, "[miniwfa_b200] mwf_wfa_chain: not built yet\n");
-	abort();
+	void *km_tmp = !(opt->flag & MWF_F_NO_KALLOC) ? km_init2(km, 0) : 0; /* scratch arena, as the reference's km_wfa (:857) */
+	const int want_cigar = !!(opt->flag & MWF_F_CIGAR);
+	int32_t n_a, i, x0 = 0, y0 = 0, n_job = 0, score = 0;
+	uint64_t *a = chain_anchors(km_tmp, tl, ts, ql, qs, opt->kmer, opt->max_occ, &n_a);
+	seg_t *seg;
+	cigbuf_t c = { 0, 0, 0 };
+
+	n_a = drop_short_runs(n_a, a, tl, ql, opt->kmer, opt->min_len);
+	seg = (seg_t*)kmalloc(km_tmp, sizeof(seg_t) * ((size_t)n_a + 1));
+	for (i = 0; i <= n_a; ++i) { /* classify what lies between consecutive anchors (:861-889) */
+		seg_t *g = &seg[i];
+		const int32_t x1 = i == n_a ? tl : (int32_t)(a[i] >> 32) + 1, y1 = i == n_a ? ql : (int32_t)(uint32_t)a[i] + 1;
+		g->x0 = x0, g->y0 = y0, g->x1 = x1, g->y1 = y1, g->job = -1;
+		if (i < n_a && x1 - x0 == y1 - y0 && x1 - x0 <= opt->kmer) g->kind = SEG_MATCH; /* inside overlapping k-mer matches */
+		else if (x0 < x1 && y0 < y1) {
+			if (x1 - x0 >= 10000 && y1 - y0 >= 10000 && kmer_similarity(km, x1 - x0, ts + x0, y1 - y0, qs + y0, opt->kmer) < 0.02)
+				g->kind = SEG_TWO_GAPS; /* two long unrelated stretches: a deletion and an insertion (:869-874) */
+			else g->kind = SEG_EXACT, g->job = n_job++;
+		} else if (x0 < x1) g->kind = SEG_DEL;
+		else if (y0 < y1) g->kind = SEG_INS;
+		else g->kind = SEG_NONE;
+		x0 = x1, y0 = y1;
+	}
+	{ /* all exact gap fills in one submission (the reference loops over mwf_wfa_exact, :877) */
+		int32_t *jtl = (int32_t*)kmalloc(km_tmp, sizeof(int32_t) * (size_t)(n_job + 1)), *jql = (int32_t*)kmalloc(km_tmp, sizeof(int32_t) * (size_t)(n_job + 1));
+		const char **jts = (const char**)kmalloc(km_tmp, sizeof(char*) * (size_t)(n_job + 1)), **jqs = (const char**)kmalloc(km_tmp, sizeof(char*) * (size_t)(n_job + 1));
+		mwf_rst_t *jr = (mwf_rst_t*)kcalloc(km_tmp, (size_t)(n_job + 1), sizeof(mwf_rst_t));
+		for (i = 0; i <= n_a; ++i)
+			if (seg[i].kind == SEG_EXACT) {
+				const int32_t j = seg[i].job;
+				jtl[j] = seg[i].x1 - seg[i].x0, jts[j] = ts + seg[i].x0;
+				jql[j] = seg[i].y1 - seg[i].y0, jqs[j] = qs + seg[i].y0;
+			}
+		if (n_job > 0) mwf_wfa_exact_batch(km_tmp, opt, n_job, jtl, jts, jql, jqs, jr);
+		for (i = 0; i <= n_a; ++i) { /* concatenate in order */
+			const seg_t *g = &seg[i];
+			const int32_t dx = g->x1 - g->x0, dy = g->y1 - g->y0;
+			switch (g->kind) {
+			case SEG_MATCH:
+				if (want_cigar) cig_add(km, &c, 7, dx);
+				break;
+			case SEG_TWO_GAPS:
+				if (want_cigar) cig_add(km, &c, 2, dx), cig_add(km, &c, 1, dy);
+				score += opt->o2 * 2 + opt->e2 * (dx + dy);
+				break;
+			case SEG_EXACT:
+				if (want_cigar) cig_cat(km, &c, jr[g->job].n_cigar, jr[g->job].cigar);
+				score += jr[g->job].s;
+				kfree(km_tmp, jr[g->job].cigar);
+				break;
+			case SEG_DEL: /* the reference records these two even in score-only mode (:883, :886) */
+				cig_add(km, &c, 2, dx);
+				score += one_gap_cost(opt, dx);
+				break;
+			case SEG_INS:
+				cig_add(km, &c, 1, dy);
+				score += one_gap_cost(opt, dy);
+				break;
+			default: break;
+			}
+		}
+		kfree(km_tmp, jr); kfree(km_tmp, (void*)jqs); kfree(km_tmp, (void*)jts); kfree(km_tmp, jql); kfree(km_tmp, jtl);
+	}
+	kfree(km_tmp, seg);
+	kfree(km_tmp, a);
+	if (km_tmp) km_destroy(km_tmp);
+	r->s = score;
+	r->n_cigar = c.n;
+	r->cigar = (uint32_t*)krelocate(km, c.w, sizeof(uint32_t) * (size_t)c.n);
 }

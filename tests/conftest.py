@@ -33,3 +33,16 @@ def case_inputs(case):
     if "synth" in case:
         return synth.make_pair(*case["synth"])
     return case["t"].encode("latin-1"), case["q"].encode("latin-1")
+
+
+@pytest.fixture(scope="session")
+def golden_chain():
+    with open(os.path.join(ROOT, "tests", "golden", "golden_chain.json")) as f:
+        return json.load(f)["cases"]
+
+
+def chain_case_inputs(case):
+    """Inputs of a golden_chain.json case from its recipe (same builder as the generator script)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_chain
+    return make_golden_chain.build_inputs(case)

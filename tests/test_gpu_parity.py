@@ -5,7 +5,7 @@ import random
 
 import pytest
 
-from conftest import case_inputs
+from conftest import case_inputs, chain_case_inputs
 import miniwfa_b200 as mw
 from miniwfa_b200 import synth
 from miniwfa_b200.api import cigar_string
@@ -207,3 +207,51 @@ def test_batch_object_reuse_and_timers():
             b.wait()
             assert b.fetch() == want
         assert b.kernel_ms > 0 and b.launches >= 1 and b.h2d_bytes > 8 * 40000
+
+
+def test_chain_and_auto_golden(golden, golden_chain):
+    """mwf_wfa_chain / mwf_wfa_auto (host chaining + one GPU batch of gap fills) against the reference's own output:
+    score, CIGAR words and the n_iter the reference leaves in the result."""
+    mw.set_kernel(mw.KERNEL_AUTO)
+    import ctypes
+    L = mw.lib()
+    n = 0
+    for c in list(golden_chain) + [c for c in golden if c.get("fn", "mwf_wfa_exact") != "mwf_wfa_exact"]:
+        t, q = chain_case_inputs(c) if "recipe" in c else case_inputs(c)
+        o = mw.opt_init(**c["opt"])
+        r = mw.MwfRst()
+        getattr(L, c["fn"])(None, ctypes.byref(o), len(t), t, len(q), q, ctypes.byref(r))
+        cig = [r.cigar[i] for i in range(r.n_cigar)]
+        if r.cigar:
+            L.kfree(None, r.cigar)
+        e = c["expect"]
+        assert (r.s, r.n_cigar, r.n_iter, cigar_string(cig)) == (e["s"], e["n_cigar"], e["n_iter"], e["cigar"]), c["name"]
+        if c["opt"].get("flag", 0) & 1:
+            assert mw.cigar2score(o, cig)[1:] == (len(t), len(q)), c["name"]
+        n += 1
+    assert n >= 40
+
+
+def test_cli_matches_reference_output(tmp_path):
+    """test-mwf over two FASTA files (two records each): PAF-like lines as the reference prints them (main.c:73-80)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(mw.api.LIB_PATH), "test-mwf")
+    assert os.path.exists(exe)
+    t3 = ("CAGGGGCAGACTGACACTTCACACGGCCGGGTACTCTAACAGACCTGCAGCTGAGGGTCCT",
+          "TAGGGGCAGACTGACACCTCACACGGCCGGGTACTCCTCTGAGACAAAACTTCCAGAGGAACGATCAGACAGCAGCATTCGCGGTTCATGAAAATCCGCTGTTCTG"
+          "CAGCCACCGCTGCTGGTACCCAGGCAAACAGGGTCTAGAGTGGACCTTTAGCAAACTCCAACAGACCTGCAGCTGAGGGTCCT")
+    f1, f2 = tmp_path / "a.fa", tmp_path / "b.fa"
+    f1.write_text(">t3-0 first\n%s\n%s\n>x\nACGT\n" % (t3[0][:30], t3[0][30:]))
+    f2.write_text(">t3-1\n%s\n>y\nACCT\n" % t3[1])
+    want = {"": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t155", "x\t4\t0\t4\t+\ty\t4\t0\t4\t4"],
+            "-c": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t155\t1X16=1X14=128I4=1X24=", "x\t4\t0\t4\t+\ty\t4\t0\t4\t4\t2=1X1="],
+            "-cp5": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t155\t1X16=1X14=128I4=1X24=", "x\t4\t0\t4\t+\ty\t4\t0\t4\t4\t2=1X1="],
+            "-cu": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t155\t1X16=1X18=128I1X24="],
+            "-ct": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t155\t1X16=1X14=128I4=1X24="],
+            "-ca": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t272\t1X16=1X18=118I1=10I24="]}
+    for flags, lines in want.items():
+        out = subprocess.run([exe] + ([flags] if flags else []) + [str(f1), str(f2)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        got = out.stdout.strip().split("\n")
+        assert got[:len(lines)] == lines, (flags, got)
