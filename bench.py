@@ -290,8 +290,10 @@ def main():
     value = ns_total / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region -------------------------
+    host_bufs = mw.api.host_arrays(pairs)  # the caller's host buffers (plain C arrays of pointers and lengths), built once
+
     def e2e_step():
-        with mw.Batch(opt, pairs) as bb:   # exactly what mwf_wfa_exact_batch() does, kept open to read its byte counters
+        with mw.Batch(opt, pairs, arrays=host_bufs) as bb:   # exactly what mwf_wfa_exact_batch() does, kept open to read its byte counters
             bb.upload()
             bb.run()
             rr = bb.fetch()

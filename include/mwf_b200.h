@@ -55,6 +55,8 @@ void mwf_b200_set_device(int dev);
 int  mwf_b200_get_device(void);
 /* force a kernel family (tests/bench); default: $MWF_B200_KERNEL ("cta"/"grid"/"tile"), else AUTO */
 void mwf_b200_set_kernel(int kernel);
+/* device and pinned-host workspaces are cached across batches; this frees every cached buffer */
+void mwf_b200_release_cache(void);
 /* threads per CTA for subsequently created batches (0 = default) */
 void mwf_b200_set_block_threads(int threads);
 

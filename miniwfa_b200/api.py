@@ -62,6 +62,8 @@ def lib():
             getattr(L, "mwf_b200_batch_" + name).restype = i64
         L.mwf_b200_batch_kernel_used.argtypes = [vp]
         L.mwf_b200_batch_kernel_used.restype = ctypes.c_int
+        L.mwf_b200_release_cache.argtypes = []
+        L.mwf_b200_release_cache.restype = None
         L.kfree.argtypes = [vp, vp]
         L.km_init.restype = vp
         L.km_destroy.argtypes = [vp]
@@ -122,6 +124,11 @@ def _arrays(pairs):
     return n, tl, ts, ql, qs
 
 
+def host_arrays(pairs):
+    """The C arrays (n, tl[], ts[], ql[], qs[]) mwf_wfa_exact_batch / mwf_b200_batch_* take, built once."""
+    return _arrays(pairs)
+
+
 def wfa_exact_batch(opt, pairs, km=None):
     """mwf_wfa_exact_batch over [(ts, qs), ...] -> list of (s, n_cigar, n_iter, [cigar words])."""
     n, tl, ts, ql, qs = _arrays(pairs)
@@ -133,8 +140,9 @@ def wfa_exact_batch(opt, pairs, km=None):
 class Batch:
     """mwf_b200_batch_*: create -> upload -> run -> wait -> fetch, with the engine's own timers."""
 
-    def __init__(self, opt, pairs):
-        self.n, self._tl, self._ts, self._ql, self._qs = _arrays(pairs)
+    def __init__(self, opt, pairs, arrays=None):
+        """arrays: the host buffers of `pairs` as returned by host_arrays(pairs), to build them only once."""
+        self.n, self._tl, self._ts, self._ql, self._qs = arrays if arrays is not None else _arrays(pairs)
         self.opt = opt
         self.h = lib().mwf_b200_batch_create(ctypes.byref(opt), self.n, self._tl, self._ql)
 

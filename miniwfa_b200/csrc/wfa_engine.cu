@@ -36,6 +36,8 @@
 #include <algorithm>
 #include <vector>
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 #include "mwf_b200.h"
 #include "kalloc.h"
 
@@ -761,6 +763,89 @@ static int pick_kernel_pref(void)
 	return k;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* workspace cache: device and pinned-host buffers survive mwf_b200_batch_destroy and are handed */
+/* to the next batch of a similar size, so that a one-shot mwf_wfa_exact_batch() call does not   */
+/* pay cudaMalloc / cudaMallocHost / cudaFree every time ("own them in the shim, */
+/* lazily created").  mwf_b200_release_cache() gives everything back.                            */
+/* ------------------------------------------------------------------------------------------ */
+
+struct WsEntry { void *p; size_t bytes; int dev; bool host; };
+static std::mutex g_ws_mu;
+static std::vector<WsEntry> g_ws_free;                 /* oldest first */
+static std::unordered_map<void*, WsEntry> g_ws_live;
+
+static void ws_really_free(const WsEntry &e)
+{
+	if (e.host) cudaFreeHost(e.p);
+	else { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(e.dev); cudaFree(e.p); cudaSetDevice(cur); }
+}
+
+extern "C" void mwf_b200_release_cache(void)
+{
+	std::lock_guard<std::mutex> lk(g_ws_mu);
+	for (size_t i = 0; i < g_ws_free.size(); ++i) ws_really_free(g_ws_free[i]);
+	g_ws_free.clear();
+}
+
+static size_t ws_cached_bytes(int dev)
+{
+	std::lock_guard<std::mutex> lk(g_ws_mu);
+	size_t t = 0;
+	for (size_t i = 0; i < g_ws_free.size(); ++i)
+		if (!g_ws_free[i].host && g_ws_free[i].dev == dev) t += g_ws_free[i].bytes;
+	return t;
+}
+
+/* returns true when the memory is fresh (never used by an earlier batch) */
+static bool ws_alloc(void **out, size_t bytes, bool host, int dev)
+{
+	bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+	{
+		std::lock_guard<std::mutex> lk(g_ws_mu);
+		for (size_t i = 0; i < g_ws_free.size(); ++i) {
+			const WsEntry e = g_ws_free[i];
+			if (e.host == host && (host || e.dev == dev) && e.bytes >= bytes && e.bytes <= bytes + bytes / 4 + 65536) {
+				g_ws_free.erase(g_ws_free.begin() + i);
+				g_ws_live[e.p] = e;
+				*out = e.p;
+				return false;
+			}
+		}
+	}
+	void *p = 0;
+	cudaError_t err = host ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
+	if (err == cudaErrorMemoryAllocation) { /* give the cached buffers back and try once more */
+		cudaGetLastError();
+		mwf_b200_release_cache();
+		err = host ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
+	}
+	CUDA_OK(err);
+	WsEntry e = { p, bytes, dev, host };
+	std::lock_guard<std::mutex> lk(g_ws_mu);
+	g_ws_live[p] = e;
+	*out = p;
+	return true;
+}
+
+static void ws_free(void *p)
+{
+	if (p == 0) return;
+	std::vector<WsEntry> drop;
+	{
+		std::lock_guard<std::mutex> lk(g_ws_mu);
+		std::unordered_map<void*, WsEntry>::iterator it = g_ws_live.find(p);
+		if (it == g_ws_live.end()) return;
+		g_ws_free.push_back(it->second);
+		g_ws_live.erase(it);
+		while (g_ws_free.size() > 48) { drop.push_back(g_ws_free.front()); g_ws_free.erase(g_ws_free.begin()); }
+	}
+	for (size_t i = 0; i < drop.size(); ++i) ws_really_free(drop[i]);
+}
+
+template<class T> static bool ws_dev(T **out, size_t bytes, int dev) { return ws_alloc((void**)out, bytes, false, dev); }
+template<class T> static bool ws_host(T **out, size_t bytes) { return ws_alloc((void**)out, bytes, true, 0); }
+
 struct mwf_b200_batch {
 	int dev, kernel, n, n_sm, threads, n_slots;
 	mwf_opt_t opt;
@@ -789,7 +874,7 @@ struct mwf_b200_batch {
 	int64_t launches, h2d, d2h;
 	bool ran;
 	/* tile engine (wfa_tile.cuh) */
-	int tW, tHL, tT, tR, tNT, wave_pairs, tile_grid;
+	int tW, tHL, tT, tR, tNT, wave_pairs, tile_grid, s_limit;
 	size_t tile_smem, items_cap;
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
@@ -859,6 +944,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
 		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
 	b->seq_bytes = off + 64, b->cigar_words = cw;
+	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
 
 	/* kernel family */
 	int pref = pick_kernel_pref();
@@ -887,18 +973,17 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	CUDA_OK(cudaEventCreate(&b->ev1));
 
 	/* device workspaces */
-	CUDA_OK(cudaMalloc(&b->d_seq, b->seq_bytes));
-	CUDA_OK(cudaMallocHost(&b->h_seq, b->seq_bytes));
-	memset(b->h_seq, 0, b->seq_bytes);
-	CUDA_OK(cudaMalloc(&b->d_pairs, sizeof(PairDesc) * std::max(1, n_pairs)));
-	CUDA_OK(cudaMalloc(&b->d_outs, sizeof(PairOut) * std::max(1, n_pairs)));
-	CUDA_OK(cudaMallocHost(&b->h_outs, sizeof(PairOut) * std::max(1, n_pairs)));
-	CUDA_OK(cudaMalloc(&b->d_order, sizeof(int) * std::max(1, n_pairs)));
-	CUDA_OK(cudaMalloc(&b->d_ctl, 64));
+	ws_dev(&b->d_seq, b->seq_bytes, b->dev);
+	if (ws_host(&b->h_seq, b->seq_bytes)) memset(b->h_seq, 0, b->seq_bytes); /* padding bytes are never interpreted: runs are clamped */
+	ws_dev(&b->d_pairs, sizeof(PairDesc) * std::max(1, n_pairs), b->dev);
+	ws_dev(&b->d_outs, sizeof(PairOut) * std::max(1, n_pairs), b->dev);
+	ws_host(&b->h_outs, sizeof(PairOut) * std::max(1, n_pairs));
+	ws_dev(&b->d_order, sizeof(int) * std::max(1, n_pairs), b->dev);
+	ws_dev(&b->d_ctl, 64, b->dev);
 	b->d_ring = 0, b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
 	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_tmisc = 0, b->h_running = 0;
 	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0, b->wave_pairs = 0;
-	if (b->is_tb) CUDA_OK(cudaMalloc(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw)));
+	if (b->is_tb) ws_dev(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw), b->dev);
 	if (pref == MWF_B200_KERNEL_TILE) {
 		/* state: two buffers of R rows per pair in flight; pairs beyond the memory budget run in later waves */
 		b->pitch = (int)((max_len + 2LL * n + 2LL * b->tHL + 32 + b->tW + 31) & ~31LL);
@@ -907,28 +992,31 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			sizeof(int2) * ((size_t)b->pitch / umax + 2);
 		size_t free_b = 0, total_b = 0;
 		CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
 		const double frac = b->is_tb ? 0.35 : 0.85;
 		b->wave_pairs = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_pairs), (size_t)(free_b * frac) / per_pair));
 		const int wp = b->wave_pairs;
-		CUDA_OK(cudaMalloc(&b->d_state, (size_t)wp * 2 * b->tR * b->pitch * 4));
-		CUDA_OK(cudaMemsetAsync(b->d_state, 0xC0, (size_t)wp * 2 * b->tR * b->pitch * 4, b->stream)); /* a large negative int32 everywhere */
-		CUDA_OK(cudaMalloc(&b->d_alive, (size_t)wp * b->pitch * 4));
-		CUDA_OK(cudaMalloc(&b->d_tctl, sizeof(TileCtl) * wp));
+		if (ws_dev(&b->d_state, (size_t)wp * 2 * b->tR * b->pitch * 4, b->dev)) /* fresh memory: a large negative int32 everywhere */
+			CUDA_OK(cudaMemsetAsync(b->d_state, 0xC0, (size_t)wp * 2 * b->tR * b->pitch * 4, b->stream));
+		ws_dev(&b->d_alive, (size_t)wp * b->pitch * 4, b->dev);
+		ws_dev(&b->d_tctl, sizeof(TileCtl) * wp, b->dev);
 		b->items_cap = (size_t)wp * ((size_t)b->pitch / umax + 2);
-		CUDA_OK(cudaMalloc(&b->d_items, sizeof(int2) * b->items_cap));
-		CUDA_OK(cudaMalloc(&b->d_tmisc, 128));
-		CUDA_OK(cudaMallocHost(&b->h_running, 2 * sizeof(int)));
+		ws_dev(&b->d_items, sizeof(int2) * b->items_cap, b->dev);
+		ws_dev(&b->d_tmisc, 128, b->dev);
+		ws_host(&b->h_running, 2 * sizeof(int));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
 		if (b->is_tb) {
-			CUDA_OK(cudaMalloc(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * wp));
+			ws_dev(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * wp, b->dev);
 			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+			free_b += ws_cached_bytes(b->dev);
+		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
 			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
 			long long worst = (max_sbound + 2) * (max_len + 2LL * n + 2LL * b->tT + 16);
 			worst = std::max((worst + 255) & ~255LL, 65536LL);
 			b->arena_total = (long long)std::min((double)budget, (double)worst * wp) & ~255LL;
 			if (b->arena_total < 4096) die("not enough free device memory for the traceback arena");
-			CUDA_OK(cudaMalloc(&b->d_arena, (size_t)b->arena_total));
+			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		}
 		int per_sm = 0;
 		if (b->is_tb) {
@@ -943,20 +1031,22 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	} else {
 		b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
 		b->ring_stride = (long long)n * 5 * b->pitch;
-		CUDA_OK(cudaMalloc(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots));
+		ws_dev(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);
 		if (b->is_tb) {
 			b->rowtab_stride = max_sbound + 2;
-			CUDA_OK(cudaMalloc(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots));
+			ws_dev(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots, b->dev);
 			if (seg) {
-				CUDA_OK(cudaMalloc(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots));
+				ws_dev(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);
 				b->snap_cap = (int)(max_sbound / opt->step + 2);
-				CUDA_OK(cudaMalloc(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots));
-				CUDA_OK(cudaMalloc(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots));
-				CUDA_OK(cudaMalloc(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots));
+				ws_dev(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots, b->dev);
+				ws_dev(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots, b->dev);
+				ws_dev(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots, b->dev);
 			}
 			/* traceback / snapshot arena: the worst case when it is small, else most of what is free */
 			size_t free_b = 0, total_b = 0;
 			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+			free_b += ws_cached_bytes(b->dev);
+		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
 			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
 			long long worst = (max_sbound + 2) * (max_len + 16);
 			if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
@@ -964,7 +1054,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
 			if (per_slot < 4096) die("not enough free device memory for the traceback arena");
 			b->arena_total = per_slot * b->n_slots;
-			CUDA_OK(cudaMalloc(&b->d_arena, (size_t)b->arena_total));
+			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		}
 	}
 	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false;
@@ -1046,6 +1136,7 @@ static void run_tile(mwf_b200_batch_t *b)
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.seg = 0, P.seg_stride = 0;
+	P.s_limit = b->s_limit;
 	{ /* row tables */
 		const int n = b->pen.nring, d1 = b->pen.e1 + 1, d2 = b->pen.e2 + 1, rb = b->tW * 4;
 		const int bE1 = n, bF1 = bE1 + d1, bE2 = bF1 + d1, bF2 = bE2 + d2;
@@ -1182,11 +1273,12 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 {
 	if (!b) return;
 	CUDA_OK(cudaSetDevice(b->dev));
-	cudaFree(b->d_seq); cudaFreeHost(b->h_seq); cudaFree(b->d_pairs); cudaFree(b->d_outs); cudaFreeHost(b->h_outs);
-	cudaFree(b->d_order); cudaFree(b->d_ctl); cudaFree(b->d_ring); cudaFree(b->d_ring2); cudaFree(b->d_arena);
-	cudaFree(b->d_rowtab); cudaFree(b->d_snapoff); cudaFree(b->d_snaphdr); cudaFree(b->d_seg); cudaFree(b->d_cigar);
-	cudaFree(b->d_tctl); cudaFree(b->d_state); cudaFree(b->d_alive); cudaFree(b->d_items); cudaFree(b->d_tmisc);
-	if (b->h_running) { cudaFreeHost(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
+	CUDA_OK(cudaStreamSynchronize(b->stream)); /* the workspaces go back to the cache: nothing may still use them */
+	ws_free(b->d_seq); ws_free(b->h_seq); ws_free(b->d_pairs); ws_free(b->d_outs); ws_free(b->h_outs);
+	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
+	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc);
+	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
 	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
 	if (b->own_stream) cudaStreamDestroy(b->stream);
 	delete b;

@@ -70,6 +70,7 @@ struct TParams {
 	long long rowtab_stride;
 	const int *seg;            /* pass-2 checkpoints (s,d) per pair, or null */
 	int seg_stride;
+	int s_limit;               /* no alignment of the batch can cost more (all-gap bound): a guard against endless runs */
 	/* byte offsets of the rows a score touches inside a tile, by score modulo the ring depths (wf_next_prep, :252-257) */
 	int4 tabH[TILE_NRING_MAX];  /* [s % nring]  = {H[s-x], H[s-o1-e1], H[s-o2-e2], H[s]} */
 	int4 tabE1[TILE_EDEPTH_MAX]; /* [s % (e1+1)] = {E1[s-e1], F1[s-e1], E1[s], F1[s]} */
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 		}
 	}
 	if (threadIdx.x != 0) return;
+	if (status == TS_RUN && s > P.s_limit) status = TS_SHRINK; /* cannot happen: the all-gap alignment costs less */
 	if (status == TS_RUN) { /* cut the next block */
 		int sid = c->sid;
 		if (P.seg && sid < c->n_seg && P.seg[(size_t)slot * P.seg_stride + 2 * sid] == s) { /* band collapse (:413-416) */
@@ -511,7 +513,11 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ T
 				tile_cells<MODE, false>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
 				if (MODE == MODE_TB) { if (useful) __stcs(reinterpret_cast<uint32_t*>(tbp), tbw); tbp += tb_pitch; }
 				if (t > t_alive) alive_bits |= alive4(d0, tl, ql, nh, ve1, vf1, ve2, vf2);
+#ifndef TILE_NOBAR_EXPERIMENT
 				__syncthreads();
+#else
+				__syncwarp();
+#endif
 			}
 		} else {
 			for (int t = 1; t <= Tb; ++t) {
