@@ -874,7 +874,8 @@ struct mwf_b200_batch {
 	int64_t launches, h2d, d2h;
 	bool ran;
 	/* tile engine (wfa_tile.cuh) */
-	int tW, tHL, tT, tR, tNT, wave_pairs, tile_grid, s_limit;
+	int tW, tHL, tT, tR, tNT, tCPT, wave_pairs, tile_grid, s_limit;
+	tile_kernel_fn tile_fn;
 	size_t tile_smem, items_cap;
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
@@ -949,15 +950,21 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	/* kernel family */
 	int pref = pick_kernel_pref();
 	const int n = b->pen.nring;
-	b->tT = env_int("MWF_B200_TILE_T", 64) & ~3;
+	/* tile geometry: many pairs -> 4 cells per thread, 128 threads, blocks of 32 scores (lowest instruction count per cell, most
+	 * CTAs per SM); few pairs -> 1 cell per thread, 512 threads on a 512-wide tile: the GPU is not full anyway, and the dependent
+	 * chain of one score step is 4x shorter */
+	const bool few = n_pairs < 16;
+	b->tCPT = env_int("MWF_B200_TILE_CPT", few ? 1 : 4);
+	if (b->tCPT != 1 && b->tCPT != 2 && b->tCPT != 4) die("MWF_B200_TILE_CPT must be 1, 2 or 4");
+	b->tT = env_int("MWF_B200_TILE_T", few ? 64 : 32) & ~3;
 	b->tT = std::max(4, std::min(b->tT, TILE_TMAX));
 	b->tHL = b->tT;
-	b->tNT = env_int("MWF_B200_TILE_THREADS", 256);
-	b->tW = 4 * b->tNT;
+	b->tNT = env_int("MWF_B200_TILE_THREADS", few ? 512 : 128);
+	b->tW = b->tCPT * b->tNT;
 	b->tR = n + 2 * (opt->e1 + 1) + 2 * (opt->e2 + 1);
 	b->tile_smem = (size_t)b->tR * b->tW * 4 + 64;
 	const int umax = b->tW - 2 * b->tHL;
-	const bool tile_ok = !seg && n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 &&
+	const bool tile_ok = !seg && n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 && b->tW % 4 == 0 &&
 		b->tile_smem <= (size_t)prop.sharedMemPerBlockOptin && umax / 2 - 4 >= 2 * b->tHL + n + 8;
 	if (pref == MWF_B200_KERNEL_TILE && !tile_ok) pref = MWF_B200_KERNEL_AUTO;
 	if (pref == MWF_B200_KERNEL_AUTO) {
@@ -995,6 +1002,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
 		const double frac = b->is_tb ? 0.35 : 0.85;
 		b->wave_pairs = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_pairs), (size_t)(free_b * frac) / per_pair));
+		if (env_int("MWF_B200_TILE_WAVE", 0) > 0) b->wave_pairs = std::min(b->wave_pairs, env_int("MWF_B200_TILE_WAVE", 0)); /* tests */
 		const int wp = b->wave_pairs;
 		if (ws_dev(&b->d_state, (size_t)wp * 2 * b->tR * b->pitch * 4, b->dev)) /* fresh memory: a large negative int32 everywhere */
 			CUDA_OK(cudaMemsetAsync(b->d_state, 0xC0, (size_t)wp * 2 * b->tR * b->pitch * 4, b->stream));
@@ -1019,13 +1027,9 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		}
 		int per_sm = 0;
-		if (b->is_tb) {
-			CUDA_OK(cudaFuncSetAttribute(wfa_tile_kernel<MODE_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem));
-			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfa_tile_kernel<MODE_TB>, b->tNT, b->tile_smem));
-		} else {
-			CUDA_OK(cudaFuncSetAttribute(wfa_tile_kernel<MODE_SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem));
-			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfa_tile_kernel<MODE_SCORE>, b->tNT, b->tile_smem));
-		}
+		b->tile_fn = tile_kernel_for(b->is_tb, b->tCPT);
+		CUDA_OK(cudaFuncSetAttribute(b->tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem));
+		CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->tile_fn, b->tNT, b->tile_smem));
 		if (per_sm < 1) die("tile kernel does not fit on an SM");
 		b->tile_grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
 	} else {
@@ -1164,8 +1168,7 @@ static void run_tile(mwf_b200_batch_t *b)
 		for (int chunk = 0;; ++chunk) {
 			for (int k = 0; k < chunk_len; ++k, ++it) {
 				wfa_plan_kernel<<<np, 128, 0, b->stream>>>(P, it);
-				if (b->is_tb) wfa_tile_kernel<MODE_TB><<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
-				else wfa_tile_kernel<MODE_SCORE><<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
+				b->tile_fn<<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
 				b->launches += 2;
 			}
 			CUDA_OK(cudaGetLastError());

@@ -176,15 +176,18 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 	const int tl = pd.tl, ql = pd.ql, n = P.pen.nring, doff = tile_doff(P, tl);
 	int status = TS_RUN, s = c->s, wflo = c->wflo, wfhi = c->wfhi;
 	if (c->Tb > 0) { /* replay, in the order of miniwfa.c:419-426 */
+		__shared__ int widths[TILE_TMAX];
+		if (threadIdx.x < c->Tb) widths[threadIdx.x] = c->hi_log[threadIdx.x] - c->lo_log[threadIdx.x] + 1; /* all loads in flight at once */
+		__syncthreads();
 		if (threadIdx.x == 0) {
 			long long n_iter = c->n_iter;
-			const int Tb = c->Tb, s0 = c->s;
+			const int Tb = c->Tb, s0 = c->s, done_t = c->done_t;
 			int last = 0;
 			for (int t = 1; t <= Tb; ++t) {
-				n_iter += c->hi_log[t - 1] - c->lo_log[t - 1] + 1;
+				n_iter += widths[t - 1];
 				s = s0 + t;
 				if ((P.max_iter > 0 && n_iter > P.max_iter) || (P.max_s > 0 && s > P.max_s)) { status = TS_STOPPED; break; }
-				if (c->done_t == t) { status = TS_DONE; last = c->done_last; break; }
+				if (done_t == t) { status = TS_DONE; last = c->done_last; break; }
 			}
 			c->n_iter = n_iter, c->s = s, c->last = last;
 			c->wflo = c->fin_lo, c->wfhi = c->fin_hi, c->cur ^= 1;
@@ -268,22 +271,39 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 /* the tile kernel                                                                             */
 /* ------------------------------------------------------------------------------------------ */
 
-/* shared-memory accesses with explicit 32-bit shared addresses (one add per row, no generic-address arithmetic) */
-__device__ __forceinline__ int4 lds4(uint32_t a)
+/* shared-memory accesses with explicit 32-bit shared addresses (one add per row, no generic-address arithmetic);
+ * N = 1, 2 or 4 consecutive int32 */
+template<int N> __device__ __forceinline__ void ldsv(uint32_t a, int (&v)[N]);
+template<> __device__ __forceinline__ void ldsv<4>(uint32_t a, int (&v)[4])
 {
-	int4 v;
-	asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-	return v;
+	asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a) : "memory");
+}
+template<> __device__ __forceinline__ void ldsv<2>(uint32_t a, int (&v)[2])
+{
+	asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(a) : "memory");
+}
+template<> __device__ __forceinline__ void ldsv<1>(uint32_t a, int (&v)[1])
+{
+	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[0]) : "r"(a) : "memory");
+}
+template<int N> __device__ __forceinline__ void stsv(uint32_t a, const int (&v)[N]);
+template<> __device__ __forceinline__ void stsv<4>(uint32_t a, const int (&v)[4])
+{
+	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+template<> __device__ __forceinline__ void stsv<2>(uint32_t a, const int (&v)[2])
+{
+	asm volatile("st.shared.v2.b32 [%0], {%1,%2};" :: "r"(a), "r"(v[0]), "r"(v[1]) : "memory");
+}
+template<> __device__ __forceinline__ void stsv<1>(uint32_t a, const int (&v)[1])
+{
+	asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v[0]) : "memory");
 }
 __device__ __forceinline__ int lds1(uint32_t a)
 {
 	int v;
 	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
 	return v;
-}
-__device__ __forceinline__ void sts4(uint32_t a, int x, int y, int z, int w)
-{
-	asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
 /* 4 bytes of a sequence starting at byte `pos` (the funnel shift takes its amount modulo 32) */
@@ -293,51 +313,67 @@ __device__ __forceinline__ uint32_t seq4(const uint32_t *__restrict__ w, int pos
 	return __funnelshift_r(__ldg(p), __ldg(p + 1), pos << 3);
 }
 
-/* continue a match run: everything up to k is known to match (wf_extend1_padded, miniwfa.c:212-226), clamped to kmax */
+/* continue a match run: everything up to k is known to match (wf_extend1_padded, miniwfa.c:212-226), clamped to kmax.
+ * 16 bytes of each sequence per round, all ten loads in flight together: on the optimal path a run is ~1/divergence bases long
+ * and this loop is the serial part of a score step. */
 __device__ __noinline__ int tile_extend_more(const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q, int k, int d, int kmax)
 {
 	while (k < kmax) {
-		const uint32_t x = seq4(T, k + 1) ^ seq4(Q, d + k + 1);
-		if (x) { k += (__ffs(x) - 1) >> 3; break; }
-		k += 4;
+		const int tp = k + 1, qp = d + k + 1;
+		const uint32_t *tw = T + (tp >> 2), *qw = Q + (qp >> 2);
+		uint32_t a[5], b[5];
+#pragma unroll
+		for (int i = 0; i < 5; ++i) a[i] = __ldg(tw + i), b[i] = __ldg(qw + i);
+		int adv = 16;
+#pragma unroll
+		for (int i = 3; i >= 0; --i) {
+			const uint32_t x = __funnelshift_r(a[i], a[i + 1], tp << 3) ^ __funnelshift_r(b[i], b[i + 1], qp << 3);
+			if (x) adv = 4 * i + ((__ffs(x) - 1) >> 3);
+		}
+		k += adv;
+		if (adv < 16) break;
 	}
 	return min(k, kmax);
 }
 
-/* one score step for the 4 diagonals of this thread; sb = shared address of the tile + 16 * tid.
+/* what one score step leaves in registers for the caller: the new cells of this thread */
+template<int CPT> struct CellOut { int H[CPT], E1[CPT], F1[CPT], E2[CPT], F2[CPT]; uint32_t tb; };
+
+/* one score step for the CPT consecutive diagonals of this thread; sb = shared address of the tile + 4 * CPT * tid.
  * qh = {Hx, Ho1, Ho2, nH}, q1 = {pE1, pF1, nE1, nF1}, q2 = {pE2, pF2, nE2, nF2}: byte offsets of the rows (wf_next_prep, :252-257).
+ * The d-1 / d+1 neighbours come from registers inside the thread, from warp shuffles across threads, and from two
+ * scalar shared loads across warps.
  * EDGE = false: the whole warp lies strictly inside the band and does not hold the terminal diagonal,
  * so no masking, no edge rule, no termination test. */
-template<int MODE, bool EDGE>
+template<int MODE, bool EDGE, int CPT>
 __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int4 &q1, const int4 &q2, int d0, int lo_t, int hi_t, int dfin, int tl,
-                                          const int (&kmin)[4], const int (&kspan)[4],
+                                          const int (&kmin)[CPT], const int (&kspan)[CPT],
                                           const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
-                                          bool no_left, bool no_right, bool useful, uint32_t &tbw_out,
-                                          int4 &oH, int4 &oE1, int4 &oF1, int4 &oE2, int4 &oF2)
+                                          bool no_left, bool no_right, bool useful, CellOut<CPT> &o)
 {
 	const int lane = threadIdx.x & 31;
-	const int4 ho1 = lds4(sb + qh.y), pe1 = lds4(sb + q1.x), pf1 = lds4(sb + q1.y), ho2 = lds4(sb + qh.z);
-	const int4 pe2 = lds4(sb + q2.x), pf2 = lds4(sb + q2.y), hx = lds4(sb + qh.x);
-	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
+	int ho1[CPT], pe1[CPT], pf1[CPT], ho2[CPT], pe2[CPT], pf2[CPT], hx[CPT];
+	ldsv<CPT>(sb + qh.y, ho1); ldsv<CPT>(sb + q1.x, pe1); ldsv<CPT>(sb + q1.y, pf1); ldsv<CPT>(sb + qh.z, ho2);
+	ldsv<CPT>(sb + q2.x, pe2); ldsv<CPT>(sb + q2.y, pf2); ldsv<CPT>(sb + qh.x, hx);
+	int A1[CPT + 2], A2[CPT + 2], C1[CPT + 2], C2[CPT + 2], bA1[CPT + 2], bA2[CPT + 2], bC1[CPT + 2], bC2[CPT + 2];
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		const int o1 = I4(ho1, j), o2 = I4(ho2, j), e1 = I4(pe1, j), e2 = I4(pe2, j), f1 = I4(pf1, j), f2 = I4(pf2, j);
-		A1[j + 1] = max(o1, e1), A2[j + 1] = max(o2, e2);
-		C1[j + 1] = max(o1, f1), C2[j + 1] = max(o2, f2); /* the +1 of F is applied below */
-		if (MODE != MODE_SCORE) bA1[j + 1] = o1 < e1, bA2[j + 1] = o2 < e2, bC1[j + 1] = o1 < f1, bC2[j + 1] = o2 < f2;
+	for (int j = 0; j < CPT; ++j) {
+		A1[j + 1] = max(ho1[j], pe1[j]), A2[j + 1] = max(ho2[j], pe2[j]);
+		C1[j + 1] = max(ho1[j], pf1[j]), C2[j + 1] = max(ho2[j], pf2[j]); /* the +1 of F is applied below */
+		if (MODE != MODE_SCORE) bA1[j + 1] = ho1[j] < pe1[j], bA2[j + 1] = ho2[j] < pe2[j], bC1[j + 1] = ho1[j] < pf1[j], bC2[j + 1] = ho2[j] < pf2[j];
 	}
-	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
-	A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
-	C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
-	C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	A1[0] = __shfl_up_sync(0xffffffffu, A1[CPT], 1);
+	A2[0] = __shfl_up_sync(0xffffffffu, A2[CPT], 1);
+	C1[CPT + 1] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+	C2[CPT + 1] = __shfl_down_sync(0xffffffffu, C2[1], 1);
 	if (MODE != MODE_SCORE) {
-		const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+		const int bl = __shfl_up_sync(0xffffffffu, bA1[CPT] | bA2[CPT] << 1, 1);
 		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
-		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[CPT + 1] = br & 1, bC2[CPT + 1] = br >> 1;
 	}
 	if (lane == 0 || lane == 31) { /* the neighbour belongs to another warp (or to nobody: stale halo) */
 		const bool left = lane == 0;
-		const uint32_t nb = sb + (left ? -4 : 16);
+		const uint32_t nb = sb + (left ? -4 : 4 * CPT);
 		int o1 = NEG_INF, x1 = NEG_INF, o2 = NEG_INF, x2 = NEG_INF;
 		if (!(left ? no_left : no_right)) {
 			o1 = lds1(nb + qh.y), o2 = lds1(nb + qh.z);
@@ -348,19 +384,20 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 			A1[0] = m1, A2[0] = m2;
 			if (MODE != MODE_SCORE) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
 		} else {
-			C1[5] = m1, C2[5] = m2;
-			if (MODE != MODE_SCORE) bC1[5] = o1 < x1, bC2[5] = o2 < x2;
+			C1[CPT + 1] = m1, C2[CPT + 1] = m2;
+			if (MODE != MODE_SCORE) bC1[CPT + 1] = o1 < x1, bC2[CPT + 1] = o2 < x2;
 		}
 	}
-	int vH[4], vE1[4], vF1[4], vE2[4], vF2[4], st[4] = {0, 0, 0, 0}, h0[4];
-	bool ext[4];
+	int st[CPT], h0[CPT];
+	bool ext[CPT];
 	uint32_t tbw = 0;
 	int myfl = 0;
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
+	for (int j = 0; j < CPT; ++j) {
 		int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2] + 1, F2 = C2[j + 2] + 1;
-		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = I4(hx, j) + 1;
+		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = hx[j] + 1;
 		int H = max(hxp, gmx);
+		st[j] = 0;
 		if (MODE != MODE_SCORE) { /* the 7-bit pack, miniwfa.c:290-306 */
 			const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4));
 			st[j] = z;
@@ -374,49 +411,43 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 				if (d == hi_t) myfl |= FL_HI;
 			}
 		}
-		vE1[j] = E1, vE2[j] = E2, vF1[j] = F1, vF2[j] = F2, h0[j] = H;
+		o.E1[j] = E1, o.E2[j] = E2, o.F1[j] = F1, o.F2[j] = F2, h0[j] = H;
 		ext[j] = (unsigned)(H - kmin[j]) <= (unsigned)kspan[j]; /* on the matrix (:402) */
 	}
 	/* wf_extend (:400-411): first probe of the match run, 4 bytes per sequence, all loads in flight together */
-	uint32_t px[4];
+	uint32_t px[CPT];
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
+	for (int j = 0; j < CPT; ++j) {
 		const int tp = ext[j] ? h0[j] + 1 : 0, qp = ext[j] ? d0 + j + h0[j] + 1 : 0;
 		px[j] = seq4(T, tp) ^ seq4(Q, qp);
 	}
-	oE1 = make_int4(vE1[0], vE1[1], vE1[2], vE1[3]), oF1 = make_int4(vF1[0], vF1[1], vF1[2], vF1[3]);
-	oE2 = make_int4(vE2[0], vE2[1], vE2[2], vE2[3]), oF2 = make_int4(vF2[0], vF2[1], vF2[2], vF2[3]);
-	sts4(sb + q1.z, vE1[0], vE1[1], vE1[2], vE1[3]);
-	sts4(sb + q1.w, vF1[0], vF1[1], vF1[2], vF1[3]);
-	sts4(sb + q2.z, vE2[0], vE2[1], vE2[2], vE2[3]);
-	sts4(sb + q2.w, vF2[0], vF2[1], vF2[2], vF2[3]);
+	stsv<CPT>(sb + q1.z, o.E1); stsv<CPT>(sb + q1.w, o.F1); stsv<CPT>(sb + q2.z, o.E2); stsv<CPT>(sb + q2.w, o.F2);
 	bool more = false;
-	bool unres[4];
+	bool unres[CPT];
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
+	for (int j = 0; j < CPT; ++j) {
 		const int kmax = kmin[j] + kspan[j];
 		const int adv = px[j] ? (__ffs(px[j]) - 1) >> 3 : 4;
 		const int k = min(h0[j] + adv, kmax);
 		unres[j] = ext[j] && px[j] == 0 && k < kmax;
 		more |= unres[j];
-		vH[j] = ext[j] ? k : h0[j];
+		o.H[j] = ext[j] ? k : h0[j];
 	}
 	if (more) { /* rare: a run longer than the first probe */
 #pragma unroll
-		for (int j = 0; j < 4; ++j)
-			if (unres[j]) vH[j] = tile_extend_more(T, Q, vH[j], d0 + j, kmin[j] + kspan[j]);
+		for (int j = 0; j < CPT; ++j)
+			if (unres[j]) o.H[j] = tile_extend_more(T, Q, o.H[j], d0 + j, kmin[j] + kspan[j]);
 	}
-	if (EDGE && useful && dfin >= d0 && dfin < d0 + 4) { /* end of both sequences, :405-409 */
+	if (EDGE && useful && dfin >= d0 && dfin < d0 + CPT) { /* end of both sequences, :405-409 */
 #pragma unroll
-		for (int j = 0; j < 4; ++j)
-			if (d0 + j == dfin && ext[j] && vH[j] == tl - 1) {
+		for (int j = 0; j < CPT; ++j)
+			if (d0 + j == dfin && ext[j] && o.H[j] == tl - 1) {
 				myfl |= FL_DONE;
-				if (MODE == MODE_TB && vH[j] == h0[j]) myfl |= st[j] << FL_LAST_SHIFT;
+				if (MODE == MODE_TB && o.H[j] == h0[j]) myfl |= st[j] << FL_LAST_SHIFT;
 			}
 	}
-	oH = make_int4(vH[0], vH[1], vH[2], vH[3]);
-	sts4(sb + qh.w, vH[0], vH[1], vH[2], vH[3]);
-	tbw_out = tbw;
+	stsv<CPT>(sb + qh.w, o.H);
+	o.tb = tbw;
 	return myfl;
 }
 
@@ -425,21 +456,35 @@ __device__ __forceinline__ bool on_matrix_u(int d, int k, int tl, int ql)
 	return (unsigned)(k + 1) <= (unsigned)tl && (unsigned)(d + k + 1) <= (unsigned)ql;
 }
 
-__device__ __forceinline__ int alive4(int d0, int tl, int ql, const int4 &nh, const int4 &ve1, const int4 &vf1, const int4 &ve2, const int4 &vf2)
+template<int CPT>
+__device__ __forceinline__ int alive_cells(int d0, int tl, int ql, const CellOut<CPT> &o)
 {
 	int bits = 0;
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
+	for (int j = 0; j < CPT; ++j) {
 		const int d = d0 + j;
-		if (on_matrix_u(d, I4(nh, j), tl, ql) || on_matrix_u(d, I4(ve1, j), tl, ql) || on_matrix_u(d, I4(vf1, j), tl, ql) ||
-		    on_matrix_u(d, I4(ve2, j), tl, ql) || on_matrix_u(d, I4(vf2, j), tl, ql)) bits |= 1 << j;
+		if (on_matrix_u(d, o.H[j], tl, ql) || on_matrix_u(d, o.E1[j], tl, ql) || on_matrix_u(d, o.F1[j], tl, ql) ||
+		    on_matrix_u(d, o.E2[j], tl, ql) || on_matrix_u(d, o.F2[j], tl, ql)) bits |= 1 << j;
 	}
 	return bits;
 }
 
+template<int CPT> __device__ __forceinline__ void store_tb(uint8_t *p, uint32_t w) /* CPT traceback bytes, streaming store */
+{
+	if (CPT == 4) __stcs(reinterpret_cast<uint32_t*>(p), w);
+	else if (CPT == 2) __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)w);
+	else __stcs(reinterpret_cast<unsigned char*>(p), (unsigned char)w);
+}
+
+/* threads per CTA and CTAs per SM the kernel is compiled for: 4 cells per thread keeps the instruction count per cell lowest
+ * (batches); 2 and 1 cells per thread put 2x / 4x the threads on a tile, which shortens the dependent chain of one score
+ * step when there are too few tiles to fill the GPU (single large pairs) */
+#define TILE_MAX_THREADS(CPT) ((CPT) == 4 ? 512 : 512)
+#define TILE_MIN_CTAS(CPT) ((CPT) == 4 ? 1 : 2)
+
 /* shared memory: rows[R][W] int32 | ctl ints [16] (flags, item, mbarrier) */
-template<int MODE>
-__global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ TParams P, int it)
+template<int MODE, int CPT>
+__global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa_tile_kernel(const __grid_constant__ TParams P, int it)
 {
 	extern __shared__ __align__(128) int32_t smem_tile[];
 	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
@@ -449,7 +494,7 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ T
 	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
 	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
 	const unsigned int n_items = P.cnt[it & 1].n_items;
-	const uint32_t sb = smem_u32(rows) + 16 * tid;
+	const uint32_t sb = smem_u32(rows) + 4 * CPT * tid;
 	const bool no_left = tid == 0, no_right = tid == NT - 1;
 	if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 	uint32_t phase = 0;
@@ -482,20 +527,20 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ T
 		}
 		if (tid < 3) sc[tid] = 0;
 		const uint32_t *T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), *Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off);
-		const int c = 4 * tid, d0 = idx0 + c - doff;
+		const int c = CPT * tid, d0 = idx0 + c - doff;
 		const bool useful = c >= HL && c < HL + ulen;
 		const bool special = left_edge || right_edge || (dfin >= idx0 - doff && dfin < idx0 - doff + W); /* flags matter */
-		uint8_t *tbp = 0; /* traceback byte of this thread's first diagonal at the block's first score (wf_tb_add, :33-44) */
+		uint8_t *tbp = 0; /* traceback bytes of this thread's diagonals at the block's first score (wf_tb_add, :33-44) */
 		long long tb_pitch = 0;
 		if (MODE == MODE_TB) tbp = P.arena + ctl->row_base + (idx0 + c), tb_pitch = ctl->row_size;
-		int kmin[4], kspan[4];
+		int kmin[CPT], kspan[CPT];
 #pragma unroll
-		for (int j = 0; j < 4; ++j) { /* H is on the matrix iff kmin <= H <= kmin + kspan (:402) */
+		for (int j = 0; j < CPT; ++j) { /* H is on the matrix iff kmin <= H <= kmin + kspan (:402) */
 			const int d = d0 + j, lo = max(-1, -1 - d), hi = min(tl - 1, ql - 1 - d);
 			if (hi >= lo) kmin[j] = lo, kspan[j] = hi - lo;
 			else kmin[j] = 0x3fffffff, kspan[j] = 0;
 		}
-		const int wd_lo = d0 - 4 * lane, wd_hi = wd_lo + 127;
+		const int wd_lo = d0 - CPT * lane, wd_hi = wd_lo + 32 * CPT - 1;
 		const int bnd = (s0 | 0xff) + 1; /* next band trim */
 		const int t_alive = bnd - n - s0; /* steps t > t_alive feed wf_stripe_shrink (:144-171) */
 		int alive_bits = 0;
@@ -504,20 +549,15 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ T
 		phase ^= 1;
 		__syncthreads();
 		/* ---- Tb fused next+extend steps ---- */
-		uint32_t tbw;
-		int4 nh, ve1, vf1, ve2, vf2;
+		CellOut<CPT> o;
 		if (!special) {
 			for (int t = 1; t <= Tb; ++t) {
 				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
 				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-				tile_cells<MODE, false>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
-				if (MODE == MODE_TB) { if (useful) __stcs(reinterpret_cast<uint32_t*>(tbp), tbw); tbp += tb_pitch; }
-				if (t > t_alive) alive_bits |= alive4(d0, tl, ql, nh, ve1, vf1, ve2, vf2);
-#ifndef TILE_NOBAR_EXPERIMENT
+				tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, o);
+				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
+				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
 				__syncthreads();
-#else
-				__syncwarp();
-#endif
 			}
 		} else {
 			for (int t = 1; t <= Tb; ++t) {
@@ -527,11 +567,11 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ T
 				const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
 				const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
 				if (edge) {
-					const int myfl = tile_cells<MODE, true>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
+					const int myfl = tile_cells<MODE, true, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, o);
 					if (myfl) atomicOr(&sc[t % 3], myfl);
-				} else tile_cells<MODE, false>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, tbw, nh, ve1, vf1, ve2, vf2);
-				if (MODE == MODE_TB) { if (useful) __stcs(reinterpret_cast<uint32_t*>(tbp), tbw); tbp += tb_pitch; }
-				if (t > t_alive) alive_bits |= alive4(d0, tl, ql, nh, ve1, vf1, ve2, vf2);
+				} else tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, o);
+				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
+				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
 				if (tid == 0) {
 					sc[(t + 1) % 3] = 0;
 					if (left_edge) ctl->lo_log[t - 1] = lo_t;
@@ -556,17 +596,24 @@ __global__ void __launch_bounds__(512) wfa_tile_kernel(const __grid_constant__ T
 			if (right_edge) ctl->fin_hi = wfhi_c;
 		}
 		if (Tb > t_alive && useful) { /* alive words: tag = score of the coming trim | alive bit */
-			int4 *ap = reinterpret_cast<int4*>(P.alive + (size_t)slot * pitch + idx0 + c);
-			int4 a = *ap;
-			a.x = ((a.x & ~1) == bnd ? a.x : bnd) | (alive_bits & 1);
-			a.y = ((a.y & ~1) == bnd ? a.y : bnd) | (alive_bits >> 1 & 1);
-			a.z = ((a.z & ~1) == bnd ? a.z : bnd) | (alive_bits >> 2 & 1);
-			a.w = ((a.w & ~1) == bnd ? a.w : bnd) | (alive_bits >> 3 & 1);
-			*ap = a;
+			int32_t *ap = P.alive + (size_t)slot * pitch + idx0 + c;
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) {
+				const int a = ap[j];
+				ap[j] = ((a & ~1) == bnd ? a : bnd) | (alive_bits >> j & 1);
+			}
 		}
 		if (tid < 32) bulk_wait_read(); /* the rows may be overwritten by the next item's load */
 	}
 	if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* stores complete before the CTA retires */
+}
+
+typedef void (*tile_kernel_fn)(const TParams, int);
+
+static tile_kernel_fn tile_kernel_for(bool tb, int cpt)
+{
+	if (tb) return cpt == 4 ? wfa_tile_kernel<MODE_TB, 4> : cpt == 2 ? wfa_tile_kernel<MODE_TB, 2> : wfa_tile_kernel<MODE_TB, 1>;
+	return cpt == 4 ? wfa_tile_kernel<MODE_SCORE, 4> : cpt == 2 ? wfa_tile_kernel<MODE_SCORE, 2> : wfa_tile_kernel<MODE_SCORE, 1>;
 }
 
 /* wf_traceback (miniwfa.c:329-377) for the pairs of a wave: one warp per pair */

@@ -255,3 +255,28 @@ def test_cli_matches_reference_output(tmp_path):
         assert out.returncode == 0, out.stderr
         got = out.stdout.strip().split("\n")
         assert got[:len(lines)] == lines, (flags, got)
+
+
+def test_tile_geometry_variants(monkeypatch):
+    """The tile engine under every cells-per-thread variant, several tile widths / block lengths, and with the batch cut into
+    waves: same bits as the CPU checker (the engine reads these settings when a batch is created)."""
+    mw.set_kernel(mw.KERNEL_TILE)
+    rng = random.Random(7)
+    pairs = []
+    for i in range(20):
+        n = rng.choice([50, 400, 1500, 4000, 9000])
+        t = bytes(rng.choice(b"ACGT") for _ in range(n))
+        pairs.append((t, mutate(rng, t, rng.choice([0.01, 0.05, 0.2]))))
+    modes = ({}, {"flag": mw.F_CIGAR}, {"flag": mw.F_CIGAR, "x": 2, "o1": 3, "e1": 1, "o2": 9, "e2": 1}, {"max_iter": 300000})
+    want = {i: [orc.checker_exact(orc.make_opt(**kw), t, q) for t, q in pairs] for i, kw in enumerate(modes)}
+    for cpt, nt, T, wave in ((4, 256, 64, 0), (4, 128, 32, 7), (2, 256, 32, 0), (2, 512, 64, 3), (1, 512, 64, 0), (1, 256, 24, 0), (4, 64, 16, 0), (2, 96, 12, 5)):
+        monkeypatch.setenv("MWF_B200_TILE_CPT", str(cpt))
+        monkeypatch.setenv("MWF_B200_TILE_THREADS", str(nt))
+        monkeypatch.setenv("MWF_B200_TILE_T", str(T))
+        monkeypatch.setenv("MWF_B200_TILE_WAVE", str(wave))
+        for i, kw in enumerate(modes):
+            with mw.Batch(mw.opt_init(**kw), pairs) as b:
+                assert b.kernel_used == mw.KERNEL_TILE, (cpt, nt, T)
+                b.upload()
+                b.run()
+                assert b.fetch() == want[i], (cpt, nt, T, wave, kw)

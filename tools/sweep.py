@@ -10,8 +10,11 @@ npairs = int(os.environ.get("NP", "128"))
 pairs = synth.make_batch(npairs, 100000, 0.05, 0)
 single = [synth.make_pair(150000, 0.038, 900000)]
 ref = None
-configs = [tuple(int(x) for x in c.split(",")) for c in sys.argv[1:]] or [(64, 256, 8)]
-for T, NT, CPS in configs:
+configs = [tuple(int(x) for x in c.split(",")) for c in sys.argv[1:]] or [(64, 256, 8, 4)]
+for cfg in configs:
+    T, NT, CPS = cfg[:3]
+    CPT = cfg[3] if len(cfg) > 3 else 4
+    os.environ["MWF_B200_TILE_CPT"] = str(CPT)
     os.environ["MWF_B200_TILE_T"] = str(T)
     os.environ["MWF_B200_TILE_THREADS"] = str(NT)
     os.environ["MWF_B200_TILE_CTAS_PER_SM"] = str(CPS)
@@ -32,4 +35,4 @@ for T, NT, CPS in configs:
                 if ref is None:
                     ref = key
                 assert key == ref or os.environ.get("NOASSERT")
-    print("T=%d NT=%d CPS=%d :: %s" % (T, NT, CPS, " | ".join(out)), flush=True)
+    print("T=%d NT=%d CPS=%d CPT=%d :: %s" % (T, NT, CPS, CPT, " | ".join(out)), flush=True)
