@@ -876,6 +876,8 @@ struct mwf_b200_batch {
 	/* tile engine (wfa_tile.cuh) */
 	int tW, tHL, tT, tR, tNT, tCPT, wave_pairs, tile_grid, s_limit;
 	tile_kernel_fn tile_fn;
+	long long max_len, max_sbound;
+	int *d_nseg;
 	size_t tile_smem, items_cap;
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
@@ -896,6 +898,51 @@ static long long gap_cost(const mwf_opt_t *o, long long len)
 	if (len <= 0) return 0;
 	const long long a = o->o1 + len * (long long)o->e1, b = o->o2 + len * (long long)o->e2;
 	return a < b ? a : b;
+}
+
+/* workspaces of the streaming kernels (ring in HBM): low-memory mode of any size, tiny pairs */
+static void alloc_streaming(mwf_b200_batch_t *b)
+{
+	const mwf_opt_t *opt = &b->opt;
+	const int n = b->pen.nring;
+	const bool seg = b->is_tb && opt->step > 0;
+	const long long max_len = b->max_len, max_sbound = b->max_sbound;
+	b->n_slots = b->kernel == MWF_B200_KERNEL_GRID ? 1 : std::max(1, std::min(b->n, b->n_sm));
+	b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
+	b->ring_stride = (long long)n * 5 * b->pitch;
+	ws_dev(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);
+	if (b->is_tb) {
+		b->rowtab_stride = max_sbound + 2;
+		ws_dev(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots, b->dev);
+		if (seg) {
+			ws_dev(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);
+			b->snap_cap = (int)(max_sbound / opt->step + 2);
+			ws_dev(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots, b->dev);
+			ws_dev(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots, b->dev);
+			ws_dev(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots, b->dev);
+		}
+		/* traceback / snapshot arena: the worst case when it is small, else most of what is free */
+		size_t free_b = 0, total_b = 0;
+		CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+		free_b += ws_cached_bytes(b->dev);
+		const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
+		long long worst = (max_sbound + 2) * (max_len + 16);
+		if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
+		worst = std::max((worst + 255) & ~255LL, 65536LL);
+		long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
+		if (per_slot < 4096) die("not enough free device memory for the traceback arena");
+		b->arena_total = per_slot * b->n_slots;
+		ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
+	}
+}
+
+/* give the tile engine's workspaces back (the low-memory pass did not fit the arena: the streaming kernels take over) */
+static void free_tile(mwf_b200_batch_t *b)
+{
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_rowtab); ws_free(b->d_arena); ws_free(b->d_seg);
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_tmisc = 0, b->d_nseg = 0, b->d_rowtab = 0, b->d_arena = 0, b->d_seg = 0;
+	b->arena_total = 0, b->rowtab_stride = 0;
 }
 
 extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t n_pairs, const int32_t *tl, const int32_t *ql)
@@ -946,6 +993,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
 	b->seq_bytes = off + 64, b->cigar_words = cw;
 	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
+	b->max_len = max_len, b->max_sbound = max_sbound, b->d_nseg = 0;
 
 	/* kernel family */
 	int pref = pick_kernel_pref();
@@ -964,7 +1012,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	b->tR = n + 2 * (opt->e1 + 1) + 2 * (opt->e2 + 1);
 	b->tile_smem = (size_t)b->tR * b->tW * 4 + 64;
 	const int umax = b->tW - 2 * b->tHL;
-	const bool tile_ok = !seg && n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 && b->tW % 4 == 0 &&
+	const bool tile_ok = n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 && b->tW % 4 == 0 &&
 		b->tile_smem <= (size_t)prop.sharedMemPerBlockOptin && umax / 2 - 4 >= 2 * b->tHL + n + 8;
 	if (pref == MWF_B200_KERNEL_TILE && !tile_ok) pref = MWF_B200_KERNEL_AUTO;
 	if (pref == MWF_B200_KERNEL_AUTO) {
@@ -1014,15 +1062,20 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		ws_host(&b->h_running, 2 * sizeof(int));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
+		if (seg) { /* low-memory mode: checkpoints found by walking a high-memory pass (wfa_tile_checkpoint_kernel) */
+			b->snap_cap = (int)(max_sbound / opt->step + 2);
+			ws_dev(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * wp, b->dev);
+			ws_dev(&b->d_nseg, sizeof(int) * wp, b->dev);
+		}
 		if (b->is_tb) {
 			ws_dev(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * wp, b->dev);
 			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
 			free_b += ws_cached_bytes(b->dev);
-		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
 			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
 			long long worst = (max_sbound + 2) * (max_len + 2LL * n + 2LL * b->tT + 16);
 			worst = std::max((worst + 255) & ~255LL, 65536LL);
 			b->arena_total = (long long)std::min((double)budget, (double)worst * wp) & ~255LL;
+			if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) b->arena_total = std::min<long long>(b->arena_total, env_int("MWF_B200_TILE_ARENA_MAX", 0)); /* tests */
 			if (b->arena_total < 4096) die("not enough free device memory for the traceback arena");
 			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		}
@@ -1032,35 +1085,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->tile_fn, b->tNT, b->tile_smem));
 		if (per_sm < 1) die("tile kernel does not fit on an SM");
 		b->tile_grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
-	} else {
-		b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
-		b->ring_stride = (long long)n * 5 * b->pitch;
-		ws_dev(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);
-		if (b->is_tb) {
-			b->rowtab_stride = max_sbound + 2;
-			ws_dev(&b->d_rowtab, sizeof(long long) * b->rowtab_stride * b->n_slots, b->dev);
-			if (seg) {
-				ws_dev(&b->d_ring2, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);
-				b->snap_cap = (int)(max_sbound / opt->step + 2);
-				ws_dev(&b->d_snaphdr, sizeof(int) * (size_t)b->snap_cap * (2 + 2 * n) * b->n_slots, b->dev);
-				ws_dev(&b->d_snapoff, sizeof(long long) * (size_t)b->snap_cap * b->n_slots, b->dev);
-				ws_dev(&b->d_seg, sizeof(int) * (size_t)b->snap_cap * 2 * b->n_slots, b->dev);
-			}
-			/* traceback / snapshot arena: the worst case when it is small, else most of what is free */
-			size_t free_b = 0, total_b = 0;
-			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-			free_b += ws_cached_bytes(b->dev);
-		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
-			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
-			long long worst = (max_sbound + 2) * (max_len + 16);
-			if (seg) worst = std::max(worst, (long long)b->snap_cap * (5LL * n * (max_len + 1) * 4 + 16));
-			worst = std::max((worst + 255) & ~255LL, 65536LL);
-			long long per_slot = std::min(worst, (budget / b->n_slots) & ~255LL);
-			if (per_slot < 4096) die("not enough free device memory for the traceback arena");
-			b->arena_total = per_slot * b->n_slots;
-			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
-		}
-	}
+	} else alloc_streaming(b);
 	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false;
 	return b;
 }
@@ -1126,9 +1151,43 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
 	++b->launches;
 }
 
-/* the tile engine's host loop: plan + tile kernels per time block, until every pair of the wave has ended.
+/* one pass of the tile engine over a wave of pairs: score 0, then plan + tile kernels per time block until every pair has ended.
  * The number of running pairs is read back one chunk of launches behind, so the device never waits for the host. */
-static void run_tile(mwf_b200_batch_t *b)
+static void tile_pass(mwf_b200_batch_t *b, const TParams &P, int np)
+{
+	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
+	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
+	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
+	wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(P);
+	CUDA_OK(cudaGetLastError());
+	++b->launches;
+	int it = 0;
+	for (int chunk = 0;; ++chunk) {
+		for (int k = 0; k < chunk_len; ++k, ++it) {
+			wfa_plan_kernel<<<np, 128, 0, b->stream>>>(P, it);
+			b->tile_fn<<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
+			b->launches += 2;
+		}
+		CUDA_OK(cudaGetLastError());
+		if (env_int("MWF_B200_DEBUG", 0)) {
+			TileCtl h;
+			CUDA_OK(cudaStreamSynchronize(b->stream));
+			CUDA_OK(cudaMemcpy(&h, b->d_tctl, sizeof(h), cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[tile dbg] it=%d status=%d s=%d band=[%d,%d] cur=%d n_iter=%lld Tb=%d A4=%d total4=%d n_tiles=%d done_t=%d fin=[%d,%d] lo0=%d hi0=%d sid=%d\n",
+			        it, h.status, h.s, h.wflo, h.wfhi, h.cur, h.n_iter, h.Tb, h.A4, h.total4, h.n_tiles, h.done_t, h.fin_lo, h.fin_hi, h.lo_log[0], h.hi_log[0], h.sid);
+		}
+		CUDA_OK(cudaMemcpyAsync(&b->h_running[chunk & 1], P.n_running, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaEventRecord(b->evc[chunk & 1], b->stream));
+		if (chunk >= 1) {
+			CUDA_OK(cudaEventSynchronize(b->evc[(chunk - 1) & 1]));
+			if (b->h_running[(chunk - 1) & 1] == 0) break;
+		}
+	}
+}
+
+/* the tile engine over all waves of a batch; false when a low-memory request did not fit the arena (nothing is lost: the
+ * caller reruns the batch on the streaming kernels) */
+static bool run_tile(mwf_b200_batch_t *b)
 {
 	TParams P;
 	memset(&P, 0, sizeof(P));
@@ -1139,7 +1198,6 @@ static void run_tile(mwf_b200_batch_t *b)
 	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32);
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
-	P.seg = 0, P.seg_stride = 0;
 	P.s_limit = b->s_limit;
 	{ /* row tables */
 		const int n = b->pen.nring, d1 = b->pen.e1 + 1, d2 = b->pen.e2 + 1, rb = b->tW * 4;
@@ -1155,43 +1213,33 @@ static void run_tile(mwf_b200_batch_t *b)
 			P.tabE2[e] = make_int4((bE2 + pe) * rb, (bF2 + pe) * rb, (bE2 + e) * rb, (bF2 + e) * rb);
 		}
 	}
-	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
+	const bool lowmem = b->is_tb && b->opt.step > 0;
+	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int p0 = 0; p0 < b->n; p0 += b->wave_pairs) {
 		const int np = std::min(b->wave_pairs, b->n - p0);
 		P.pair0 = p0, P.n_pairs = np;
-		CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
-		CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
-		wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(P);
-		CUDA_OK(cudaGetLastError());
-		++b->launches;
-		int it = 0;
-		for (int chunk = 0;; ++chunk) {
-			for (int k = 0; k < chunk_len; ++k, ++it) {
-				wfa_plan_kernel<<<np, 128, 0, b->stream>>>(P, it);
-				b->tile_fn<<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
-				b->launches += 2;
-			}
+		if (lowmem) {
+			/* low-memory mode (miniwfa.c:603-615).  Pass 1 of the reference only serves to find the checkpoints; here they come
+			 * from an unbanded high-memory pass (no stop tests, like mwf_wfa_seg) whose traceback bytes are walked backwards. */
+			P.seg_use = 0, P.max_s = 0, P.max_iter = 0;
+			tile_pass(b, P, np);
+			CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
+			CUDA_OK(cudaStreamSynchronize(b->stream));
+			for (int i = p0; i < p0 + np; ++i)
+				if (b->h_outs[b->order[i]].status == ST_ARENA) return false; /* s^2 bytes do not fit: the caller falls back */
+			wfa_tile_checkpoint_kernel<<<np, 32, 0, b->stream>>>(P);
 			CUDA_OK(cudaGetLastError());
-			if (env_int("MWF_B200_DEBUG", 0)) {
-				TileCtl h;
-				CUDA_OK(cudaStreamSynchronize(b->stream));
-				CUDA_OK(cudaMemcpy(&h, b->d_tctl, sizeof(h), cudaMemcpyDeviceToHost));
-				fprintf(stderr, "[tile dbg] it=%d status=%d s=%d band=[%d,%d] cur=%d n_iter=%lld Tb=%d A4=%d total4=%d n_tiles=%d done_t=%d fin=[%d,%d] lo0=%d hi0=%d\n",
-				        it, h.status, h.s, h.wflo, h.wfhi, h.cur, h.n_iter, h.Tb, h.A4, h.total4, h.n_tiles, h.done_t, h.fin_lo, h.fin_hi, h.lo_log[0], h.hi_log[0]);
-			}
-			CUDA_OK(cudaMemcpyAsync(&b->h_running[chunk & 1], P.n_running, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-			CUDA_OK(cudaEventRecord(b->evc[chunk & 1], b->stream));
-			if (chunk >= 1) {
-				CUDA_OK(cudaEventSynchronize(b->evc[(chunk - 1) & 1]));
-				if (b->h_running[(chunk - 1) & 1] == 0) break;
-			}
+			++b->launches;
+			P.seg_use = 1, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter; /* pass 2: mwf_wfa_core with the checkpoints */
 		}
+		tile_pass(b, P, np);
 		if (b->is_tb) {
 			wfa_tile_traceback_kernel<<<np, 32, 0, b->stream>>>(P);
 			CUDA_OK(cudaGetLastError());
 			++b->launches;
 		}
 	}
+	return true;
 }
 
 extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
@@ -1200,8 +1248,13 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 	b->launches = 0;
 	CUDA_OK(cudaEventRecord(b->ev0, b->stream));
 	if (b->n > 0) {
+		if (b->kernel == MWF_B200_KERNEL_TILE && !run_tile(b)) { /* low-memory request too large for a high-memory pass */
+			CUDA_OK(cudaStreamSynchronize(b->stream));
+			free_tile(b);
+			b->kernel = (b->n >= b->n_sm / 4 || b->max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
+			alloc_streaming(b);
+		}
 		if (b->kernel == MWF_B200_KERNEL_TILE) {
-			run_tile(b);
 		} else if (b->kernel == MWF_B200_KERNEL_CTA) {
 			launch_cta(b, make_params(b, b->n_slots), b->n_slots);
 		} else {
@@ -1280,7 +1333,7 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	ws_free(b->d_seq); ws_free(b->h_seq); ws_free(b->d_pairs); ws_free(b->d_outs); ws_free(b->h_outs);
 	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
 	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
-	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc);
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
 	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
 	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
 	if (b->own_stream) cudaStreamDestroy(b->stream);

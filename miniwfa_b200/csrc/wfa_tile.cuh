@@ -35,7 +35,7 @@
 enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4 };
 
 struct TileCtl { /* per pair, lives in HBM for the whole run */
-	int status, s, wflo, wfhi, cur, last, sid, n_seg;
+	int status, s, wflo, wfhi, cur, last, sid, copied;
 	long long n_iter;
 	/* the block in flight */
 	int Tb, A4, total4, n_tiles;
@@ -68,8 +68,9 @@ struct TParams {
 	unsigned long long *arena_used;
 	long long *rowtab;         /* [n_pairs][rowtab_stride] */
 	long long rowtab_stride;
-	const int *seg;            /* pass-2 checkpoints (s,d) per pair, or null */
-	int seg_stride;
+	int *seg;                  /* checkpoints (s,d) per pair [n_pairs][seg_stride] (low-memory mode), or null */
+	int *n_seg;                /* [n_pairs] */
+	int seg_stride, seg_use, step; /* seg_use: this pass collapses the band at the checkpoints (pass 2, miniwfa.c:413-416) */
 	int s_limit;               /* no alignment of the batch can cost more (all-gap bound): a guard against endless runs */
 	/* byte offsets of the rows a score touches inside a tile, by score modulo the ring depths (wf_next_prep, :252-257) */
 	int4 tabH[TILE_NRING_MAX];  /* [s % nring]  = {H[s-x], H[s-o1-e1], H[s-o2-e2], H[s]} */
@@ -150,7 +151,7 @@ __global__ void wfa_tile_init_kernel(const TParams P)
 		const int k = extend_run(T, Q, -1, 0, min(pd.tl - 1, pd.ql - 1));
 		st[doff] = k; /* H of score 0 lives in slot 0 */
 		TileCtl *c = P.ctl + slot;
-		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->n_seg = 0, c->n_iter = 0;
+		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = 0;
 		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0;
 		c->status = (k == pd.tl - 1 && k == pd.ql - 1) ? TS_DONE : TS_RUN;
 		if (c->status == TS_DONE) {
@@ -223,21 +224,28 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 	if (threadIdx.x != 0) return;
 	if (status == TS_RUN && s > P.s_limit) status = TS_SHRINK; /* cannot happen: the all-gap alignment costs less */
 	if (status == TS_RUN) { /* cut the next block */
-		int sid = c->sid;
-		if (P.seg && sid < c->n_seg && P.seg[(size_t)slot * P.seg_stride + 2 * sid] == s) { /* band collapse (:413-416) */
-			wflo = wfhi = P.seg[(size_t)slot * P.seg_stride + 2 * sid + 1];
-			++sid;
+		int sid = c->sid, Tb, copy_only = 0;
+		const int n_seg = P.seg_use ? P.n_seg[slot] : 0;
+		const int *seg = P.seg + (size_t)slot * P.seg_stride;
+		if (sid < n_seg && seg[2 * sid] == s) { /* band collapse (:413-416) */
+			if (!c->copied) copy_only = 1, c->copied = 1; /* first bring both state buffers to the same contents: the narrow blocks
+			                                                  that follow store only their own columns, but still read the wide slices */
+			else {
+				wflo = wfhi = seg[2 * sid + 1];
+				++sid, c->copied = 0;
+			}
 		}
-		int Tb = min(P.T, ((s | 0xff) + 1) - s);
-		if (P.seg && sid < c->n_seg) Tb = min(Tb, P.seg[(size_t)slot * P.seg_stride + 2 * sid] - s);
+		Tb = min(P.T, ((s | 0xff) + 1) - s);
+		if (sid < n_seg && seg[2 * sid] > s) Tb = min(Tb, seg[2 * sid] - s);
+		if (copy_only) Tb = 0;
 		if (P.max_s > 0) Tb = min(Tb, P.max_s + 1 - s);
 		if (P.is_tb) Tb = min(Tb, (int)P.rowtab_stride - 1 - s); /* no score lies beyond the all-gap alignment */
-		Tb = max(Tb, 1);
+		Tb = copy_only ? 0 : max(Tb, 1);
 		const int lo_sup = max(wflo - Tb, -tl) - n, hi_sup = min(wfhi + Tb, ql) + n;
 		const int A4 = (lo_sup + doff) & ~3, Bx = (hi_sup + doff) | 3;
 		const int total4 = (Bx - A4 + 1) >> 2, umax = P.W - 2 * P.HL;
 		const int n_tiles = (total4 * 4 + umax - 1) / umax;
-		if (P.is_tb) { /* wf_tb_add (:33-44): one row per score, here as wide as the block's superset */
+		if (P.is_tb && Tb > 0) { /* wf_tb_add (:33-44): one row per score, here as wide as the block's superset */
 			const long long rowsize = Bx - A4 + 1;
 			const unsigned long long base = atomicAdd(P.arena_used, (unsigned long long)(rowsize * Tb));
 			if ((long long)base + rowsize * Tb > P.arena_cap || s + Tb >= P.rowtab_stride) status = TS_ARENA;
@@ -614,6 +622,56 @@ static tile_kernel_fn tile_kernel_for(bool tb, int cpt)
 {
 	if (tb) return cpt == 4 ? wfa_tile_kernel<MODE_TB, 4> : cpt == 2 ? wfa_tile_kernel<MODE_TB, 2> : wfa_tile_kernel<MODE_TB, 1>;
 	return cpt == 4 ? wfa_tile_kernel<MODE_SCORE, 4> : cpt == 2 ? wfa_tile_kernel<MODE_SCORE, 2> : wfa_tile_kernel<MODE_SCORE, 1>;
+}
+
+/*
+ * Checkpoints of low-memory mode without the provenance stripe.  The reference's pass 1 (mwf_wfa_seg, miniwfa.c:551-601)
+ * carries, for every cell, the index of its ancestor in the last snapshot and chains the snapshots backwards
+ * (wf_traceback_seg, :528-549): checkpoint k is the (score, diagonal) of the last cell of the optimal path computed at or
+ * before snapshot score s_k = (k+1)*step - 1.  wf_next_seg replays exactly the choice bits of wf_next_tb (:502-523), so the
+ * same cells are met by walking the traceback bytes of an unbanded high-memory pass backwards (wf_traceback's moves,
+ * :343-366) and noting where the walk crosses each s_k -- down to score 0, through a leading gap as well.
+ * One warp per pair; no CIGAR is produced here (pass 2 does that on its own, banded, bytes).
+ */
+__global__ void wfa_tile_checkpoint_kernel(const TParams P)
+{
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot], lane = threadIdx.x & 31;
+	const TileCtl *c = P.ctl + slot;
+	if (c->status != TS_DONE) { if (lane == 0) P.n_seg[slot] = 0; return; }
+	const PairDesc pd = P.pairs[pi];
+	const uint8_t *T8 = P.seq + pd.t_off, *Q8 = P.seq + pd.q_off;
+	const long long *rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
+	const int doff = tile_doff(P, pd.tl), step = P.step;
+	const Pen pen = P.pen;
+	int *seg = P.seg + (size_t)slot * P.seg_stride;
+	int i = pd.ql - 1, k = pd.tl - 1, row = c->s, last = c->last;
+	const int n_seg = row / step; /* snapshots are taken at scores m*step - 1 < final score (:585) */
+	int ks = n_seg - 1, snap_s = n_seg * step - 1;
+	if (lane == 0) P.n_seg[slot] = n_seg;
+	while (row > 0 && ks >= 0) {
+		if (last == 0) { /* greedy backward matches (:335-341): no score, no diagonal change */
+			for (;;) {
+				const int ii = i - lane, kk = k - lane;
+				const bool same = ii >= 0 && kk >= 0 && Q8[ii] == T8[kk];
+				const unsigned m = __ballot_sync(0xffffffffu, !same);
+				if (m) { const int cnt = __ffs(m) - 1; i -= cnt, k -= cnt; break; }
+				i -= 32, k -= 32;
+			}
+		}
+		const int x = __ldcg(P.arena + rowtab[row] + (i - k + doff));
+		const int state = last == 0 ? (x & 7) : last;
+		const int ext = state > 0 ? (x >> (state + 2)) & 1 : 0;
+		if (state == 0) { --i, --k; row -= pen.x; }
+		else if (state == 1) { --i; row -= ext ? pen.e1 : pen.oe1; }
+		else if (state == 3) { --i; row -= ext ? pen.e2 : pen.oe2; }
+		else if (state == 2) { --k; row -= ext ? pen.e1 : pen.oe1; }
+		else { --k; row -= ext ? pen.e2 : pen.oe2; }
+		last = (state > 0 && ext) ? state : 0;
+		while (ks >= 0 && row <= snap_s) { /* the cell just reached is the newest one at or below this snapshot */
+			if (lane == 0) seg[2 * ks] = row, seg[2 * ks + 1] = i - k;
+			--ks, snap_s -= step;
+		}
+	}
 }
 
 /* wf_traceback (miniwfa.c:329-377) for the pairs of a wave: one warp per pair */

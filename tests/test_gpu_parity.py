@@ -280,3 +280,20 @@ def test_tile_geometry_variants(monkeypatch):
                 b.upload()
                 b.run()
                 assert b.fetch() == want[i], (cpt, nt, T, wave, kw)
+
+
+def test_lowmem_falls_back_when_the_highmem_pass_does_not_fit(monkeypatch):
+    """Low-memory requests run on the tile engine through a high-memory pass; when its s^2 traceback bytes do not fit the
+    arena the batch is rerun on the streaming two-stripe kernels.  Same bits either way."""
+    mw.set_kernel(mw.KERNEL_TILE)
+    pairs = synth.make_batch(3, 6000, 0.08, 4242)
+    kw = {"flag": mw.F_CIGAR, "step": 300}
+    want = [orc.checker_exact(orc.make_opt(**kw), t, q) for t, q in pairs]
+    for cap in (0, 200000):
+        monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", str(cap))
+        with mw.Batch(mw.opt_init(**kw), pairs) as b:
+            assert b.kernel_used == mw.KERNEL_TILE
+            b.upload()
+            b.run()
+            assert b.fetch() == want, cap
+            assert (b.kernel_used == mw.KERNEL_TILE) == (cap == 0)
