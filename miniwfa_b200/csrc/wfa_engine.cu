@@ -874,11 +874,11 @@ struct mwf_b200_batch {
 	int64_t launches, h2d, d2h;
 	bool ran;
 	/* tile engine (wfa_tile.cuh) */
-	int tW, tHL, tT, tR, tNT, tCPT, wave_pairs, tile_grid, s_limit;
-	tile_kernel_fn tile_fn;
+	struct TileGeom { int CPT, NT, T, HL, W, grid; size_t smem; tile_kernel_fn fn; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
+	int n_geom, tR, wave_pairs, s_limit;
 	long long max_len, max_sbound;
 	int *d_nseg;
-	size_t tile_smem, items_cap;
+	size_t items_cap;
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
 	int2 *d_items;
@@ -998,22 +998,31 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	/* kernel family */
 	int pref = pick_kernel_pref();
 	const int n = b->pen.nring;
-	/* tile geometry: many pairs -> 4 cells per thread, 128 threads, blocks of 32 scores (lowest instruction count per cell, most
-	 * CTAs per SM); few pairs -> 1 cell per thread, 512 threads on a 512-wide tile: the GPU is not full anyway, and the dependent
-	 * chain of one score step is 4x shorter */
-	const bool few = n_pairs < 16;
-	b->tCPT = env_int("MWF_B200_TILE_CPT", few ? 1 : 4);
-	if (b->tCPT != 1 && b->tCPT != 2 && b->tCPT != 4) die("MWF_B200_TILE_CPT must be 1, 2 or 4");
-	b->tT = env_int("MWF_B200_TILE_T", few ? 64 : 32) & ~3;
-	b->tT = std::max(4, std::min(b->tT, TILE_TMAX));
-	b->tHL = b->tT;
-	b->tNT = env_int("MWF_B200_TILE_THREADS", few ? 512 : 128);
-	b->tW = b->tCPT * b->tNT;
+	/* tile geometries.  [1] throughput: 4 cells per thread, 128 threads, blocks of 32 scores (lowest instruction count per
+	 * cell, most CTAs per SM) -- used while a launch has enough tiles to fill the GPU.  [0] latency: 1 cell per thread, 512 threads
+	 * on the same 512-wide tile, blocks of 64 scores -- used while there are few tiles (single pairs, narrow bands): the GPU is
+	 * not full anyway and the dependent chain of one score step is shorter.  The state layout does not depend on the geometry,
+	 * so run_tile switches between them from launch to launch.  The environment forces a single geometry (tests, sweeps). */
 	b->tR = n + 2 * (opt->e1 + 1) + 2 * (opt->e2 + 1);
-	b->tile_smem = (size_t)b->tR * b->tW * 4 + 64;
-	const int umax = b->tW - 2 * b->tHL;
-	const bool tile_ok = n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX && b->tNT % 32 == 0 && b->tNT >= 64 && b->tNT <= 512 && b->tW % 4 == 0 &&
-		b->tile_smem <= (size_t)prop.sharedMemPerBlockOptin && umax / 2 - 4 >= 2 * b->tHL + n + 8;
+	const bool forced = getenv("MWF_B200_TILE_CPT") || getenv("MWF_B200_TILE_T") || getenv("MWF_B200_TILE_THREADS");
+	b->n_geom = forced ? 1 : 2;
+	bool tile_ok = n <= TILE_NRING_MAX && opt->e1 < TILE_EDEPTH_MAX && opt->e2 < TILE_EDEPTH_MAX;
+	for (int g = 0; g < b->n_geom; ++g) {
+		mwf_b200_batch::TileGeom &G = b->geom[g];
+		const bool lat = forced ? n_pairs < 16 : g == 0;
+		G.CPT = env_int("MWF_B200_TILE_CPT", lat ? 1 : 4);
+		if (G.CPT != 1 && G.CPT != 2 && G.CPT != 4) die("MWF_B200_TILE_CPT must be 1, 2 or 4");
+		G.T = std::max(4, std::min(env_int("MWF_B200_TILE_T", lat ? 64 : 32) & ~3, TILE_TMAX));
+		G.HL = G.T;
+		G.NT = env_int("MWF_B200_TILE_THREADS", lat ? 512 : 128);
+		G.W = G.CPT * G.NT;
+		G.smem = (size_t)b->tR * G.W * 4 + 64;
+		G.fn = 0, G.grid = 0;
+		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)prop.sharedMemPerBlockOptin &&
+			(G.W - 2 * G.HL) / 2 - 4 >= 2 * G.HL + n + 8;
+	}
+	int umax = b->geom[0].W - 2 * b->geom[0].HL, wmax = b->geom[0].W;
+	if (b->n_geom > 1) umax = std::min(umax, b->geom[1].W - 2 * b->geom[1].HL), wmax = std::max(wmax, b->geom[1].W);
 	if (pref == MWF_B200_KERNEL_TILE && !tile_ok) pref = MWF_B200_KERNEL_AUTO;
 	if (pref == MWF_B200_KERNEL_AUTO) {
 		if (tile_ok && max_len >= env_int("MWF_B200_TILE_MINLEN", 8192)) pref = MWF_B200_KERNEL_TILE;
@@ -1041,7 +1050,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	if (b->is_tb) ws_dev(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw), b->dev);
 	if (pref == MWF_B200_KERNEL_TILE) {
 		/* state: two buffers of R rows per pair in flight; pairs beyond the memory budget run in later waves */
-		b->pitch = (int)((max_len + 2LL * n + 2LL * b->tHL + 32 + b->tW + 31) & ~31LL);
+		b->pitch = (int)((max_len + 2LL * n + 2LL * TILE_TMAX + 32 + wmax + 31) & ~31LL);
 		b->rowtab_stride = b->is_tb ? max_sbound + 2 : 0;
 		const size_t per_pair = (size_t)b->pitch * 4 * (2 * b->tR + 1) + sizeof(TileCtl) + (size_t)b->rowtab_stride * 8 +
 			sizeof(int2) * ((size_t)b->pitch / umax + 2);
@@ -1059,7 +1068,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		b->items_cap = (size_t)wp * ((size_t)b->pitch / umax + 2);
 		ws_dev(&b->d_items, sizeof(int2) * b->items_cap, b->dev);
 		ws_dev(&b->d_tmisc, 128, b->dev);
-		ws_host(&b->h_running, 2 * sizeof(int));
+		ws_host(&b->h_running, 2 * 64);
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
 		if (seg) { /* low-memory mode: checkpoints found by walking a high-memory pass (wfa_tile_checkpoint_kernel) */
@@ -1072,19 +1081,22 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
 			free_b += ws_cached_bytes(b->dev);
 			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
-			long long worst = (max_sbound + 2) * (max_len + 2LL * n + 2LL * b->tT + 16);
+			long long worst = (max_sbound + 2) * (max_len + 2LL * n + 2LL * TILE_TMAX + 16);
 			worst = std::max((worst + 255) & ~255LL, 65536LL);
 			b->arena_total = (long long)std::min((double)budget, (double)worst * wp) & ~255LL;
 			if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) b->arena_total = std::min<long long>(b->arena_total, env_int("MWF_B200_TILE_ARENA_MAX", 0)); /* tests */
 			if (b->arena_total < 4096) die("not enough free device memory for the traceback arena");
 			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		}
-		int per_sm = 0;
-		b->tile_fn = tile_kernel_for(b->is_tb, b->tCPT);
-		CUDA_OK(cudaFuncSetAttribute(b->tile_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->tile_smem));
-		CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, b->tile_fn, b->tNT, b->tile_smem));
-		if (per_sm < 1) die("tile kernel does not fit on an SM");
-		b->tile_grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
+		for (int g = 0; g < b->n_geom; ++g) {
+			mwf_b200_batch::TileGeom &G = b->geom[g];
+			int per_sm = 0;
+			G.fn = tile_kernel_for(b->is_tb, G.CPT);
+			CUDA_OK(cudaFuncSetAttribute(G.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, G.fn, G.NT, G.smem));
+			if (per_sm < 1) die("tile kernel does not fit on an SM");
+			G.grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
+		}
 	} else alloc_streaming(b);
 	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false;
 	return b;
@@ -1152,20 +1164,24 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
 }
 
 /* one pass of the tile engine over a wave of pairs: score 0, then plan + tile kernels per time block until every pair has ended.
- * The number of running pairs is read back one chunk of launches behind, so the device never waits for the host. */
-static void tile_pass(mwf_b200_batch_t *b, const TParams &P, int np)
+ * The number of running pairs and of tiles per launch is read back one chunk of launches behind, so the device never waits for
+ * the host; the tile count picks the geometry of the next chunk. */
+static void tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np)
 {
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
+	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
 	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
 	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
-	wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(P);
+	wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]);
 	CUDA_OK(cudaGetLastError());
 	++b->launches;
-	int it = 0;
+	int it = 0, g = b->n_geom > 1 && np >= 16 ? 1 : 0;
 	for (int chunk = 0;; ++chunk) {
+		const TParams &P = PP[g];
+		const mwf_b200_batch::TileGeom &G = b->geom[g];
 		for (int k = 0; k < chunk_len; ++k, ++it) {
 			wfa_plan_kernel<<<np, 128, 0, b->stream>>>(P, it);
-			b->tile_fn<<<b->tile_grid, b->tNT, b->tile_smem, b->stream>>>(P, it);
+			G.fn<<<G.grid, G.NT, G.smem, b->stream>>>(P, it);
 			b->launches += 2;
 		}
 		CUDA_OK(cudaGetLastError());
@@ -1173,14 +1189,17 @@ static void tile_pass(mwf_b200_batch_t *b, const TParams &P, int np)
 			TileCtl h;
 			CUDA_OK(cudaStreamSynchronize(b->stream));
 			CUDA_OK(cudaMemcpy(&h, b->d_tctl, sizeof(h), cudaMemcpyDeviceToHost));
-			fprintf(stderr, "[tile dbg] it=%d status=%d s=%d band=[%d,%d] cur=%d n_iter=%lld Tb=%d A4=%d total4=%d n_tiles=%d done_t=%d fin=[%d,%d] lo0=%d hi0=%d sid=%d\n",
-			        it, h.status, h.s, h.wflo, h.wfhi, h.cur, h.n_iter, h.Tb, h.A4, h.total4, h.n_tiles, h.done_t, h.fin_lo, h.fin_hi, h.lo_log[0], h.hi_log[0], h.sid);
+			fprintf(stderr, "[tile dbg] it=%d geom=%d status=%d s=%d band=[%d,%d] cur=%d n_iter=%lld Tb=%d A4=%d total4=%d n_tiles=%d done_t=%d fin=[%d,%d] lo0=%d hi0=%d sid=%d\n",
+			        it, g, h.status, h.s, h.wflo, h.wfhi, h.cur, h.n_iter, h.Tb, h.A4, h.total4, h.n_tiles, h.done_t, h.fin_lo, h.fin_hi, h.lo_log[0], h.hi_log[0], h.sid);
 		}
-		CUDA_OK(cudaMemcpyAsync(&b->h_running[chunk & 1], P.n_running, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+		int *hr = b->h_running + 16 * (chunk & 1); /* TileCounters[2] @0, n_running @32 */
+		CUDA_OK(cudaMemcpyAsync(hr, b->d_tmisc, 64, cudaMemcpyDeviceToHost, b->stream));
 		CUDA_OK(cudaEventRecord(b->evc[chunk & 1], b->stream));
 		if (chunk >= 1) {
+			const int *pr = b->h_running + 16 * ((chunk - 1) & 1);
 			CUDA_OK(cudaEventSynchronize(b->evc[(chunk - 1) & 1]));
-			if (b->h_running[(chunk - 1) & 1] == 0) break;
+			if (pr[8] == 0) break;
+			if (b->n_geom > 1) g = std::max((unsigned int)pr[0], (unsigned int)pr[2]) >= many ? 1 : 0;
 		}
 	}
 }
@@ -1194,47 +1213,52 @@ static bool run_tile(mwf_b200_batch_t *b)
 	P.pen = b->pen, P.is_tb = b->is_tb, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter;
 	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.cigar = b->d_cigar;
 	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
-	P.pitch = b->pitch, P.R = b->tR, P.W = b->tW, P.HL = b->tHL, P.T = b->tT;
+	P.pitch = b->pitch, P.R = b->tR;
 	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32);
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
-	{ /* row tables */
-		const int n = b->pen.nring, d1 = b->pen.e1 + 1, d2 = b->pen.e2 + 1, rb = b->tW * 4;
+	const bool lowmem = b->is_tb && b->opt.step > 0;
+	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
+	TParams PP[2];
+	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
+		const mwf_b200_batch::TileGeom &G = b->geom[g < b->n_geom ? g : 0];
+		const int n = b->pen.nring, d1 = b->pen.e1 + 1, d2 = b->pen.e2 + 1, rb = G.W * 4;
 		const int bE1 = n, bF1 = bE1 + d1, bE2 = bF1 + d1, bF2 = bE2 + d2;
+		TParams &Q = PP[g];
+		Q = P;
+		Q.W = G.W, Q.HL = G.HL, Q.T = G.T;
 		for (int h = 0; h < n; ++h)
-			P.tabH[h] = make_int4(((h - b->pen.x + n) % n) * rb, ((h - b->pen.oe1 + n) % n) * rb, ((h - b->pen.oe2 + n) % n) * rb, h * rb);
+			Q.tabH[h] = make_int4(((h - b->pen.x + n) % n) * rb, ((h - b->pen.oe1 + n) % n) * rb, ((h - b->pen.oe2 + n) % n) * rb, h * rb);
 		for (int e = 0; e < d1; ++e) {
 			const int pe = (e - b->pen.e1 + d1) % d1;
-			P.tabE1[e] = make_int4((bE1 + pe) * rb, (bF1 + pe) * rb, (bE1 + e) * rb, (bF1 + e) * rb);
+			Q.tabE1[e] = make_int4((bE1 + pe) * rb, (bF1 + pe) * rb, (bE1 + e) * rb, (bF1 + e) * rb);
 		}
 		for (int e = 0; e < d2; ++e) {
 			const int pe = (e - b->pen.e2 + d2) % d2;
-			P.tabE2[e] = make_int4((bE2 + pe) * rb, (bF2 + pe) * rb, (bE2 + e) * rb, (bF2 + e) * rb);
+			Q.tabE2[e] = make_int4((bE2 + pe) * rb, (bF2 + pe) * rb, (bE2 + e) * rb, (bF2 + e) * rb);
 		}
 	}
-	const bool lowmem = b->is_tb && b->opt.step > 0;
-	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int p0 = 0; p0 < b->n; p0 += b->wave_pairs) {
 		const int np = std::min(b->wave_pairs, b->n - p0);
-		P.pair0 = p0, P.n_pairs = np;
+		for (int g = 0; g < 2; ++g) PP[g].pair0 = p0, PP[g].n_pairs = np;
 		if (lowmem) {
 			/* low-memory mode (miniwfa.c:603-615).  Pass 1 of the reference only serves to find the checkpoints; here they come
 			 * from an unbanded high-memory pass (no stop tests, like mwf_wfa_seg) whose traceback bytes are walked backwards. */
-			P.seg_use = 0, P.max_s = 0, P.max_iter = 0;
-			tile_pass(b, P, np);
+			for (int g = 0; g < 2; ++g) PP[g].seg_use = 0, PP[g].max_s = 0, PP[g].max_iter = 0;
+			tile_pass(b, PP, np);
 			CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
 			CUDA_OK(cudaStreamSynchronize(b->stream));
 			for (int i = p0; i < p0 + np; ++i)
 				if (b->h_outs[b->order[i]].status == ST_ARENA) return false; /* s^2 bytes do not fit: the caller falls back */
-			wfa_tile_checkpoint_kernel<<<np, 32, 0, b->stream>>>(P);
+			wfa_tile_checkpoint_kernel<<<np, 32, 0, b->stream>>>(PP[0]);
 			CUDA_OK(cudaGetLastError());
 			++b->launches;
-			P.seg_use = 1, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter; /* pass 2: mwf_wfa_core with the checkpoints */
+			for (int g = 0; g < 2; ++g) PP[g].seg_use = 1, PP[g].max_s = b->opt.max_s, PP[g].max_iter = b->opt.max_iter; /* pass 2: mwf_wfa_core with the checkpoints */
 		}
-		tile_pass(b, P, np);
+		tile_pass(b, PP, np);
 		if (b->is_tb) {
-			wfa_tile_traceback_kernel<<<np, 32, 0, b->stream>>>(P);
+			wfa_tile_traceback_kernel<<<np, 32, 0, b->stream>>>(PP[0]);
 			CUDA_OK(cudaGetLastError());
 			++b->launches;
 		}

@@ -78,7 +78,8 @@ struct TParams {
 	int4 tabE2[TILE_EDEPTH_MAX]; /* [s % (e2+1)] = {E2[s-e2], F2[s-e2], E2[s], F2[s]} */
 };
 
-__device__ __forceinline__ int tile_doff(const TParams &P, int tl) { return tl + P.pen.nring + P.HL + 8; }
+/* index of diagonal 0 in a state row: independent of the tile geometry, so that the geometry may change between launches */
+__device__ __forceinline__ int tile_doff(const TParams &P, int tl) { return tl + P.pen.nring + TILE_TMAX + 8; }
 
 /* row index inside a state buffer / the shared-memory tile */
 struct RowMap {
