@@ -874,10 +874,18 @@ struct mwf_b200_batch {
 	int64_t launches, h2d, d2h;
 	bool ran;
 	/* tile engine (wfa_tile.cuh) */
-	struct TileGeom { int CPT, NT, T, HL, W, grid; size_t smem; tile_kernel_fn fn; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
+	struct TileGeom { int CPT, NT, T, HL, W, grid; size_t smem; tile_kernel_fn fn, fn_score; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
 	int n_geom, tR, wave_pairs, s_limit;
 	long long max_len, max_sbound;
 	int *d_nseg;
+	/* segmented traceback */
+	int seg_P;
+	int32_t *d_snap;
+	long long snap_words;
+	SnapDir *d_snapdir;
+	int snapdir_stride;
+	int *d_nsnap, *d_sstop, *h_nsnap;
+	TraceState *d_trace;
 	size_t items_cap;
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
@@ -994,6 +1002,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	b->seq_bytes = off + 64, b->cigar_words = cw;
 	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
 	b->max_len = max_len, b->max_sbound = max_sbound, b->d_nseg = 0;
+	b->seg_P = 0, b->d_snap = 0, b->snap_words = 0, b->d_snapdir = 0, b->snapdir_stride = 0, b->d_nsnap = 0, b->d_sstop = 0, b->h_nsnap = 0, b->d_trace = 0;
 
 	/* kernel family */
 	int pref = pick_kernel_pref();
@@ -1017,7 +1026,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		G.NT = env_int("MWF_B200_TILE_THREADS", lat ? 512 : 128);
 		G.W = G.CPT * G.NT;
 		G.smem = (size_t)b->tR * G.W * 4 + 64;
-		G.fn = 0, G.grid = 0;
+		G.fn = 0, G.fn_score = 0, G.grid = 0;
 		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)prop.sharedMemPerBlockOptin &&
 			(G.W - 2 * G.HL) / 2 - 4 >= 2 * G.HL + n + 8;
 	}
@@ -1092,7 +1101,9 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			mwf_b200_batch::TileGeom &G = b->geom[g];
 			int per_sm = 0;
 			G.fn = tile_kernel_for(b->is_tb, G.CPT);
+			G.fn_score = tile_kernel_for(false, G.CPT);
 			CUDA_OK(cudaFuncSetAttribute(G.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+			CUDA_OK(cudaFuncSetAttribute(G.fn_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
 			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, G.fn, G.NT, G.smem));
 			if (per_sm < 1) die("tile kernel does not fit on an SM");
 			G.grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
@@ -1166,22 +1177,22 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
 /* one pass of the tile engine over a wave of pairs: score 0, then plan + tile kernels per time block until every pair has ended.
  * The number of running pairs and of tiles per launch is read back one chunk of launches behind, so the device never waits for
  * the host; the tile count picks the geometry of the next chunk. */
-static void tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np)
+static void tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false)
 {
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
 	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
 	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
-	wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]);
+	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]); ++b->launches; }
+	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(PP[0], seg_j); ++b->launches; }
 	CUDA_OK(cudaGetLastError());
-	++b->launches;
 	int it = 0, g = b->n_geom > 1 && np >= 16 ? 1 : 0;
 	for (int chunk = 0;; ++chunk) {
 		const TParams &P = PP[g];
 		const mwf_b200_batch::TileGeom &G = b->geom[g];
 		for (int k = 0; k < chunk_len; ++k, ++it) {
 			wfa_plan_kernel<<<np, 128, 0, b->stream>>>(P, it);
-			G.fn<<<G.grid, G.NT, G.smem, b->stream>>>(P, it);
+			(score_kernel ? G.fn_score : G.fn)<<<G.grid, G.NT, G.smem, b->stream>>>(P, it);
 			b->launches += 2;
 		}
 		CUDA_OK(cudaGetLastError());
@@ -1204,9 +1215,8 @@ static void tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np)
 	}
 }
 
-/* the tile engine over all waves of a batch; false when a low-memory request did not fit the arena (nothing is lost: the
- * caller reruns the batch on the streaming kernels) */
-static bool run_tile(mwf_b200_batch_t *b)
+/* kernel parameters of the tile engine, one set per geometry */
+static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 {
 	TParams P;
 	memset(&P, 0, sizeof(P));
@@ -1218,9 +1228,7 @@ static bool run_tile(mwf_b200_batch_t *b)
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
-	const bool lowmem = b->is_tb && b->opt.step > 0;
 	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
-	TParams PP[2];
 	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
 		const mwf_b200_batch::TileGeom &G = b->geom[g < b->n_geom ? g : 0];
 		const int n = b->pen.nring, d1 = b->pen.e1 + 1, d2 = b->pen.e2 + 1, rb = G.W * 4;
@@ -1239,6 +1247,15 @@ static bool run_tile(mwf_b200_batch_t *b)
 			Q.tabE2[e] = make_int4((bE2 + pe) * rb, (bF2 + pe) * rb, (bE2 + e) * rb, (bF2 + e) * rb);
 		}
 	}
+}
+
+/* the tile engine over all waves of a batch; false when a low-memory request did not fit the arena (nothing is lost: the
+ * caller reruns the batch on the streaming kernels) */
+static bool run_tile(mwf_b200_batch_t *b)
+{
+	const bool lowmem = b->is_tb && b->opt.step > 0;
+	TParams PP[2];
+	tile_params(b, PP);
 	for (int p0 = 0; p0 < b->n; p0 += b->wave_pairs) {
 		const int np = std::min(b->wave_pairs, b->n - p0);
 		for (int g = 0; g < 2; ++g) PP[g].pair0 = p0, PP[g].n_pairs = np;
@@ -1266,13 +1283,90 @@ static bool run_tile(mwf_b200_batch_t *b)
 	return true;
 }
 
+/* High-memory CIGAR whose s^2 traceback bytes do not fit the arena (or MWF_B200_TILE_SEGP set): segmented traceback.
+ * A score-only forward pass saves the ring state every seg_P scores; then, from the last segment to the first, the state is
+ * restored, seg_P scores are recomputed with traceback bytes and the traceback warp walks that segment.  The bytes are the
+ * reference's high-memory bytes (miniwfa.c:281-308), so the CIGAR is the reference's; only seg_P rows exist at a time. */
+static void run_tile_segmented(mwf_b200_batch_t *b)
+{
+	const int wp = b->wave_pairs;
+	if (b->d_snap == 0) { /* workspaces of this mode, on first use: the big arena shrinks to make room for the snapshots */
+		CUDA_OK(cudaStreamSynchronize(b->stream));
+		ws_free(b->d_arena);
+		b->d_arena = 0;
+		mwf_b200_release_cache();
+		size_t free_b = 0, total_b = 0;
+		CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+		b->seg_P = std::max(256, env_int("MWF_B200_TILE_SEGP", 4096) & ~255);
+		b->snapdir_stride = (int)(b->max_sbound / b->seg_P + 2);
+		const long long half = (long long)((double)free_b * 0.45) & ~255LL;
+		const long long width = b->max_len + 2LL * b->pen.nring + 2LL * TILE_TMAX + 16;
+		b->arena_total = std::min(half, ((long long)(b->seg_P + 2 * TILE_TMAX) * width * wp + 255) & ~255LL);
+		b->snap_words = std::min(half, (long long)b->snapdir_stride * b->tR * width * 4 * wp) / 4;
+		if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) b->arena_total = std::max<long long>(b->arena_total, 65536);
+		ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
+		ws_dev(&b->d_snap, (size_t)b->snap_words * 4, b->dev);
+		ws_dev(&b->d_snapdir, sizeof(SnapDir) * (size_t)b->snapdir_stride * wp, b->dev);
+		ws_dev(&b->d_nsnap, sizeof(int) * wp, b->dev);
+		ws_dev(&b->d_sstop, sizeof(int) * wp, b->dev);
+		ws_dev(&b->d_trace, sizeof(TraceState) * wp, b->dev);
+		ws_host(&b->h_nsnap, sizeof(int) * wp);
+	}
+	TParams PP[2];
+	tile_params(b, PP);
+	for (int g = 0; g < 2; ++g) {
+		PP[g].snap_P = b->seg_P, PP[g].snapdir_stride = b->snapdir_stride, PP[g].snap_arena = b->d_snap, PP[g].snap_cap = b->snap_words;
+		PP[g].snap_used = (unsigned long long*)(b->d_tmisc + 72), PP[g].snapdir = b->d_snapdir, PP[g].n_snap = b->d_nsnap;
+		PP[g].trace = b->d_trace;
+	}
+	for (int p0 = 0; p0 < b->n; p0 += wp) {
+		const int np = std::min(wp, b->n - p0);
+		/* forward: scores only, stop tests as in mwf_wfa_core, snapshots every seg_P scores */
+		for (int g = 0; g < 2; ++g) {
+			PP[g].pair0 = p0, PP[g].n_pairs = np, PP[g].is_tb = 0, PP[g].snap_take = 1, PP[g].s_stop = 0;
+			PP[g].max_s = b->opt.max_s, PP[g].max_iter = b->opt.max_iter;
+		}
+		CUDA_OK(cudaMemsetAsync(b->d_nsnap, 0, sizeof(int) * np, b->stream));
+		tile_pass(b, PP, np, -1, true);
+		wfa_tile_trace_begin_kernel<<<(np + 127) / 128, 128, 0, b->stream>>>(PP[0]);
+		CUDA_OK(cudaGetLastError());
+		++b->launches;
+		CUDA_OK(cudaMemcpyAsync(b->h_nsnap, b->d_nsnap, sizeof(int) * np, cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaStreamSynchronize(b->stream));
+		int max_seg = 0;
+		for (int i = 0; i < np; ++i) {
+			if (b->h_outs[b->order[p0 + i]].status == ST_ARENA) die("device workspace exhausted (snapshots of the segmented traceback)");
+			max_seg = std::max(max_seg, b->h_nsnap[i]);
+		}
+		/* backward: one segment at a time, traceback bytes of that segment only */
+		for (int g = 0; g < 2; ++g)
+			PP[g].is_tb = 1, PP[g].snap_take = 0, PP[g].s_stop = b->d_sstop, PP[g].max_s = 0, PP[g].max_iter = 0;
+		for (int j = max_seg; j >= 0; --j) {
+			tile_pass(b, PP, np, j, false);
+			wfa_tile_trace_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
+			CUDA_OK(cudaGetLastError());
+			++b->launches;
+		}
+	}
+}
+
 extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 {
 	CUDA_OK(cudaSetDevice(b->dev));
 	b->launches = 0;
 	CUDA_OK(cudaEventRecord(b->ev0, b->stream));
 	if (b->n > 0) {
-		if (b->kernel == MWF_B200_KERNEL_TILE && !run_tile(b)) { /* low-memory request too large for a high-memory pass */
+		if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb && b->opt.step <= 0) { /* high-memory CIGAR */
+			bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
+			if (!segmented) { /* optimistic: all s^2 traceback bytes at once */
+				run_tile(b);
+				CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
+				CUDA_OK(cudaStreamSynchronize(b->stream));
+				for (int i = 0; i < b->n && !segmented; ++i) segmented = b->h_outs[i].status == ST_ARENA;
+			}
+			if (segmented) run_tile_segmented(b);
+		} else if (b->kernel == MWF_B200_KERNEL_TILE && !run_tile(b)) { /* low-memory request too large for a high-memory pass */
 			CUDA_OK(cudaStreamSynchronize(b->stream));
 			free_tile(b);
 			b->kernel = (b->n >= b->n_sm / 4 || b->max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
@@ -1358,6 +1452,7 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
 	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
 	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_snap); ws_free(b->d_snapdir); ws_free(b->d_nsnap); ws_free(b->d_sstop); ws_free(b->h_nsnap); ws_free(b->d_trace);
 	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
 	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);
 	if (b->own_stream) cudaStreamDestroy(b->stream);

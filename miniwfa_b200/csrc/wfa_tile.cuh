@@ -32,7 +32,7 @@
 #define TILE_NRING_MAX 64
 #define TILE_EDEPTH_MAX 8
 
-enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4 };
+enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4, TS_SEGEND = 5, TS_IDLE = 6 };
 
 struct TileCtl { /* per pair, lives in HBM for the whole run */
 	int status, s, wflo, wfhi, cur, last, sid, copied;
@@ -41,10 +41,17 @@ struct TileCtl { /* per pair, lives in HBM for the whole run */
 	int Tb, A4, total4, n_tiles;
 	int done_t, done_last, fin_lo, fin_hi;
 	long long row_base, row_size; /* traceback rows of the block: byte (row t, index i) at row_base + (t-1)*row_size + i */
+	long long snap_off;           /* >= 0: the tiles of this block also save the state they load (a snapshot at score s) */
+	int snap_rowsize, snap_pad;
 	int lo_log[TILE_TMAX], hi_log[TILE_TMAX];
 };
 
 struct TileCounters { unsigned int n_items, next; };
+
+/* segmented traceback: a snapshot of the ring state every snap_P scores lets the traceback bytes be
+ * recomputed one segment of snap_P scores at a time, so a CIGAR never needs s^2 bytes at once */
+struct SnapDir { int s, wflo, wfhi, A4, rowsize, pad; long long off, n_iter; };
+struct TraceState { int fwd_status, s_final, i, k, row, last, cur_op, n_out; unsigned int cur_len; int pad; long long n_iter; };
 
 struct TParams {
 	Pen pen;
@@ -72,6 +79,15 @@ struct TParams {
 	int *n_seg;                /* [n_pairs] */
 	int seg_stride, seg_use, step; /* seg_use: this pass collapses the band at the checkpoints (pass 2, miniwfa.c:413-416) */
 	int s_limit;               /* no alignment of the batch can cost more (all-gap bound): a guard against endless runs */
+	/* segmented traceback */
+	int snap_P, snapdir_stride, snap_take; /* snap_take: save a snapshot whenever s is a multiple of snap_P (a multiple of 256) */
+	int32_t *snap_arena;
+	long long snap_cap;           /* int32 words */
+	unsigned long long *snap_used;
+	SnapDir *snapdir;             /* [n_pairs][snapdir_stride] */
+	int *n_snap;                  /* [n_pairs] */
+	int *s_stop;                  /* [n_pairs] or null: a pass ends when a pair reaches this score */
+	TraceState *trace;            /* [n_pairs] */
 	/* byte offsets of the rows a score touches inside a tile, by score modulo the ring depths (wf_next_prep, :252-257) */
 	int4 tabH[TILE_NRING_MAX];  /* [s % nring]  = {H[s-x], H[s-o1-e1], H[s-o2-e2], H[s]} */
 	int4 tabE1[TILE_EDEPTH_MAX]; /* [s % (e1+1)] = {E1[s-e1], F1[s-e1], E1[s], F1[s]} */
@@ -153,7 +169,7 @@ __global__ void wfa_tile_init_kernel(const TParams P)
 		st[doff] = k; /* H of score 0 lives in slot 0 */
 		TileCtl *c = P.ctl + slot;
 		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = 0;
-		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0;
+		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1;
 		c->status = (k == pd.tl - 1 && k == pd.ql - 1) ? TS_DONE : TS_RUN;
 		if (c->status == TS_DONE) {
 			PairOut o;
@@ -224,6 +240,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 	}
 	if (threadIdx.x != 0) return;
 	if (status == TS_RUN && s > P.s_limit) status = TS_SHRINK; /* cannot happen: the all-gap alignment costs less */
+	if (status == TS_RUN && P.s_stop && s >= P.s_stop[slot]) status = TS_SEGEND; /* end of a traceback segment */
 	if (status == TS_RUN) { /* cut the next block */
 		int sid = c->sid, Tb, copy_only = 0;
 		const int n_seg = P.seg_use ? P.n_seg[slot] : 0;
@@ -240,6 +257,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 		if (sid < n_seg && seg[2 * sid] > s) Tb = min(Tb, seg[2 * sid] - s);
 		if (copy_only) Tb = 0;
 		if (P.max_s > 0) Tb = min(Tb, P.max_s + 1 - s);
+		if (P.s_stop) Tb = min(Tb, P.s_stop[slot] - s);
 		if (P.is_tb) Tb = min(Tb, (int)P.rowtab_stride - 1 - s); /* no score lies beyond the all-gap alignment */
 		Tb = copy_only ? 0 : max(Tb, 1);
 		const int lo_sup = max(wflo - Tb, -tl) - n, hi_sup = min(wfhi + Tb, ql) + n;
@@ -256,6 +274,20 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 				c->row_base = (long long)base - A4, c->row_size = rowsize;
 			}
 		}
+		c->snap_off = -1;
+		if (status == TS_RUN && P.snap_take && s > 0 && s % P.snap_P == 0 && Tb > 0) { /* the tiles save what they load */
+			const int k = s / P.snap_P - 1, rowsize = Bx - A4 + 1;
+			const long long words = (long long)P.R * rowsize;
+			const unsigned long long off = atomicAdd(P.snap_used, (unsigned long long)words);
+			if (k >= P.snapdir_stride || (long long)off + words > P.snap_cap) status = TS_ARENA;
+			else {
+				SnapDir d;
+				d.s = s, d.wflo = wflo, d.wfhi = wfhi, d.A4 = A4, d.rowsize = rowsize, d.pad = 0, d.off = (long long)off, d.n_iter = c->n_iter;
+				P.snapdir[(size_t)slot * P.snapdir_stride + k] = d;
+				P.n_snap[slot] = k + 1;
+				c->snap_off = (long long)off, c->snap_rowsize = rowsize;
+			}
+		}
 		if (status == TS_RUN) {
 			c->wflo = wflo, c->wfhi = wfhi, c->sid = sid;
 			c->Tb = Tb, c->A4 = A4, c->total4 = total4, c->n_tiles = n_tiles;
@@ -267,6 +299,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 	if (status != TS_RUN) {
 		c->status = status;
 		atomicSub(P.n_running, 1);
+		if (status == TS_SEGEND) return; /* the result record belongs to the pass that reaches the end */
 		PairOut o;
 		o.s = status == TS_DONE ? c->s : -1;
 		o.n_cigar = 0, o.n_iter = c->n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap;
@@ -308,10 +341,10 @@ template<> __device__ __forceinline__ void stsv<1>(uint32_t a, const int (&v)[1]
 {
 	asm volatile("st.shared.b32 [%0], %1;" :: "r"(a), "r"(v[0]) : "memory");
 }
-__device__ __forceinline__ int lds1(uint32_t a)
+__device__ __forceinline__ int lds1_if(uint32_t a, bool p) /* NEG_INF unless p; the load is predicated, not branched around */
 {
-	int v;
-	asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	int v = NEG_INF;
+	asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q ld.shared.b32 %0, [%1]; }" : "+r"(v) : "r"(a), "r"((int)p) : "memory");
 	return v;
 }
 
@@ -380,21 +413,17 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
 		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[CPT + 1] = br & 1, bC2[CPT + 1] = br >> 1;
 	}
-	if (lane == 0 || lane == 31) { /* the neighbour belongs to another warp (or to nobody: stale halo) */
-		const bool left = lane == 0;
+	{ /* lanes 0 and 31: the neighbour belongs to another warp (or to nobody: stale halo) -- four predicated scalar loads, no branch */
+		const bool left = lane == 0, edge_lane = (left && !no_left) || (lane == 31 && !no_right);
 		const uint32_t nb = sb + (left ? -4 : 4 * CPT);
-		int o1 = NEG_INF, x1 = NEG_INF, o2 = NEG_INF, x2 = NEG_INF;
-		if (!(left ? no_left : no_right)) {
-			o1 = lds1(nb + qh.y), o2 = lds1(nb + qh.z);
-			x1 = lds1(nb + (left ? q1.x : q1.y)), x2 = lds1(nb + (left ? q2.x : q2.y));
-		}
+		const int o1 = lds1_if(nb + qh.y, edge_lane), o2 = lds1_if(nb + qh.z, edge_lane);
+		const int x1 = lds1_if(nb + (left ? q1.x : q1.y), edge_lane), x2 = lds1_if(nb + (left ? q2.x : q2.y), edge_lane);
 		const int m1 = max(o1, x1), m2 = max(o2, x2);
-		if (left) {
-			A1[0] = m1, A2[0] = m2;
-			if (MODE != MODE_SCORE) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
-		} else {
-			C1[CPT + 1] = m1, C2[CPT + 1] = m2;
-			if (MODE != MODE_SCORE) bC1[CPT + 1] = o1 < x1, bC2[CPT + 1] = o2 < x2;
+		if (lane == 0) A1[0] = m1, A2[0] = m2;
+		if (lane == 31) C1[CPT + 1] = m1, C2[CPT + 1] = m2;
+		if (MODE != MODE_SCORE) {
+			if (lane == 0) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
+			if (lane == 31) bC1[CPT + 1] = o1 < x1, bC2[CPT + 1] = o2 < x2;
 		}
 	}
 	int st[CPT], h0[CPT];
@@ -436,7 +465,7 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 #pragma unroll
 	for (int j = 0; j < CPT; ++j) {
 		const int kmax = kmin[j] + kspan[j];
-		const int adv = px[j] ? (__ffs(px[j]) - 1) >> 3 : 4;
+		const int adv = __clz(__brev(px[j])) >> 3; /* index of the first differing byte; 4 when all four match */
 		const int k = min(h0[j] + adv, kmax);
 		unres[j] = ext[j] && px[j] == 0 && k < kmax;
 		more |= unres[j];
@@ -557,6 +586,17 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 		mbar_wait(bar, phase);
 		phase ^= 1;
 		__syncthreads();
+		if (ctl->snap_off >= 0) { /* snapshot for the segmented traceback: the state at score s0, useful columns of every row */
+			if (tid < 32) {
+				int32_t *dst = P.snap_arena + ctl->snap_off + (ustart - ctl->A4);
+				const int rs = ctl->snap_rowsize;
+				fence_async_smem();
+				for (int r = tid; r < R; r += 32) bulk_s2g(dst + (size_t)r * rs, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
+				bulk_commit();
+				bulk_wait_read();
+			}
+			__syncthreads();
+		}
 		/* ---- Tb fused next+extend steps ---- */
 		CellOut<CPT> o;
 		if (!special) {
@@ -693,5 +733,125 @@ __global__ void wfa_tile_traceback_kernel(const TParams P)
 		P.outs[pi].cigar_pos = pd.cigar_off + pd.cigar_cap - n_cigar;
 	}
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* segmented traceback: forward pass with snapshots, then segments recomputed from the end      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* after the forward (score-only) pass: remember how every pair ended and where its traceback starts */
+__global__ void wfa_tile_trace_begin_kernel(const TParams P)
+{
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= P.n_pairs) return;
+	const TileCtl *c = P.ctl + slot;
+	const PairDesc pd = P.pairs[P.order[P.pair0 + slot]];
+	TraceState t;
+	t.fwd_status = c->status, t.s_final = c->s, t.i = pd.ql - 1, t.k = pd.tl - 1, t.row = c->s, t.last = 0;
+	t.cur_op = -1, t.n_out = 0, t.cur_len = 0, t.pad = 0, t.n_iter = c->n_iter;
+	P.trace[slot] = t;
+}
+
+/* start segment j of every pair that has one: segment 0 starts at score 0 (wfa_tile_init_kernel has run), segment j > 0 at
+ * snapshot j-1, whose rows go back into state buffer 0.  grid = (n_pairs, copy CTAs) */
+__global__ void wfa_tile_segstart_kernel(const TParams P, int j)
+{
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	TileCtl *c = P.ctl + slot;
+	const TraceState *ts = P.trace + slot;
+	const int n_snap = P.n_snap[slot];
+	const bool active = ts->fwd_status == TS_DONE && j <= n_snap;
+	if (j == 0) {
+		if (blockIdx.y == 0 && threadIdx.x == 0) {
+			if (!active && c->status == TS_RUN) { c->status = TS_IDLE; atomicSub(P.n_running, 1); }
+			P.s_stop[slot] = n_snap > 0 ? P.snap_P : ts->s_final;
+		}
+		return;
+	}
+	if (!active) { if (blockIdx.y == 0 && threadIdx.x == 0) c->status = TS_IDLE; return; }
+	const SnapDir d = P.snapdir[(size_t)slot * P.snapdir_stride + (j - 1)];
+	int32_t *st = P.state + (size_t)slot * 2 * P.R * P.pitch;
+	const int32_t *src = P.snap_arena + d.off;
+	const int n4 = d.rowsize >> 2;
+	for (int r = 0; r < P.R; ++r) {
+		const int4 *s4 = reinterpret_cast<const int4*>(src + (size_t)r * d.rowsize);
+		int4 *d4 = reinterpret_cast<int4*>(st + (size_t)r * P.pitch + d.A4);
+		for (int x = blockIdx.y * blockDim.x + threadIdx.x; x < n4; x += gridDim.y * blockDim.x) d4[x] = s4[x];
+	}
+	if (blockIdx.y == 0 && threadIdx.x == 0) {
+		c->s = d.s, c->wflo = d.wflo, c->wfhi = d.wfhi, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = d.n_iter;
+		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1;
+		c->status = TS_RUN;
+		atomicAdd(P.n_running, 1);
+		P.s_stop[slot] = j == n_snap ? ts->s_final : (j + 1) * P.snap_P;
+		(void)pi;
+	}
+}
+
+/* wf_traceback (miniwfa.c:329-377) over the traceback bytes of segment j only: the walk stops when it needs a row at or
+ * below the segment's first score and resumes there in the next (earlier) segment.  One warp per pair. */
+__global__ void wfa_tile_trace_seg_kernel(const TParams P, int j)
+{
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot], lane = threadIdx.x & 31;
+	TraceState *tsp = P.trace + slot;
+	const int n_snap = P.n_snap[slot];
+	if (tsp->fwd_status != TS_DONE || j > n_snap) return;
+	const TileCtl *c = P.ctl + slot;
+	const PairDesc pd = P.pairs[pi];
+	const uint8_t *T8 = P.seq + pd.t_off, *Q8 = P.seq + pd.q_off;
+	const long long *rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
+	const int doff = tile_doff(P, pd.tl), s_lo = j * P.snap_P;
+	const Pen pen = P.pen;
+	TraceState t = *tsp;
+	if (j == n_snap) t.last = c->last; /* the pass that reached the end knows the state the path ends in (:405-409) */
+	int i = t.i, k = t.k, row = t.row, last = t.last, cur_op = t.cur_op, n_out = t.n_out;
+	uint32_t cur_len = t.cur_len;
+	uint32_t *wp = P.cigar + pd.cigar_off + pd.cigar_cap - n_out;
+#define CIG_PUSH(op_, len_) do { \
+		if ((op_) == cur_op) cur_len += (len_); \
+		else { if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; } cur_op = (op_), cur_len = (len_); } \
+	} while (0)
+	while (i >= 0 && k >= 0) {
+		if (last == 0) { /* greedy backward matches, :335-341 */
+			int run = 0;
+			for (;;) {
+				const int ii = i - lane, kk = k - lane;
+				const bool same = ii >= 0 && kk >= 0 && Q8[ii] == T8[kk];
+				const unsigned m = __ballot_sync(0xffffffffu, !same);
+				if (m) { const int cnt = __ffs(m) - 1; run += cnt, i -= cnt, k -= cnt; break; }
+				run += 32, i -= 32, k -= 32;
+			}
+			if (run > 0) CIG_PUSH(7, (uint32_t)run);
+			if (i < 0 || k < 0) break;
+		}
+		if (row <= s_lo && j > 0) break; /* this row's bytes belong to an earlier segment */
+		const int x = __ldcg(P.arena + rowtab[row] + (i - k + doff));
+		const int state = last == 0 ? (x & 7) : last;
+		const int ext = state > 0 ? (x >> (state + 2)) & 1 : 0;
+		if (state == 0) { CIG_PUSH(8, 1u); --i, --k; row -= pen.x; }
+		else if (state == 1) { CIG_PUSH(1, 1u); --i; row -= ext ? pen.e1 : pen.oe1; }
+		else if (state == 3) { CIG_PUSH(1, 1u); --i; row -= ext ? pen.e2 : pen.oe2; }
+		else if (state == 2) { CIG_PUSH(2, 1u); --k; row -= ext ? pen.e1 : pen.oe1; }
+		else { CIG_PUSH(2, 1u); --k; row -= ext ? pen.e2 : pen.oe2; }
+		last = (state > 0 && ext) ? state : 0;
+	}
+	if (j == 0 || i < 0 || k < 0) { /* the walk is over: leading gap (:368-369), flush, result record */
+		if (i >= 0) CIG_PUSH(1, (uint32_t)(i + 1));
+		else if (k >= 0) CIG_PUSH(2, (uint32_t)(k + 1));
+		if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; }
+		if (lane == 0) {
+			PairOut o;
+			o.s = t.s_final, o.n_cigar = n_out, o.n_iter = t.n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap - n_out, o.status = ST_OK, o.pad_ = 0;
+			P.outs[pi] = o;
+			tsp->fwd_status = TS_IDLE; /* nothing left to do in the remaining segments */
+		}
+		return;
+	}
+#undef CIG_PUSH
+	if (lane == 0) {
+		t.i = i, t.k = k, t.row = row, t.last = last, t.cur_op = cur_op, t.n_out = n_out, t.cur_len = cur_len;
+		*tsp = t;
+	}
+}
+
 
 #endif

@@ -297,3 +297,32 @@ def test_lowmem_falls_back_when_the_highmem_pass_does_not_fit(monkeypatch):
             b.run()
             assert b.fetch() == want, cap
             assert (b.kernel_used == mw.KERNEL_TILE) == (cap == 0)
+
+
+def test_segmented_traceback(monkeypatch):
+    """High-memory CIGAR through the segmented traceback (snapshots every P scores, segments recomputed from the end), forced
+    here with a tiny P, and reached on its own when the s^2 bytes do not fit the arena: the reference's CIGAR either way."""
+    mw.set_kernel(mw.KERNEL_TILE)
+    rng = random.Random(11)
+    pairs = [(b"ACGTACGT", b"ACGTACGT"), (b"ACGT", b""), (b"A" * 700, b"A" * 300 + b"C" * 500)]
+    for i in range(14):
+        n = rng.choice([300, 2000, 6000, 12000])
+        t = bytes(rng.choice(b"ACGT") for _ in range(n))
+        pairs.append((t, mutate(rng, t, rng.choice([0.0, 0.02, 0.1, 0.3]))))
+    modes = ({"flag": mw.F_CIGAR}, {"flag": mw.F_CIGAR, "x": 2, "o1": 3, "e1": 1, "o2": 9, "e2": 1}, {"flag": mw.F_CIGAR, "max_s": 900},
+             {"flag": mw.F_CIGAR, "max_iter": 400000})
+    want = [[orc.checker_exact(orc.make_opt(**kw), t, q) for t, q in pairs] for kw in modes]
+    for segp, cap, wave in ((256, 0, 0), (512, 0, 5), (1024, 0, 0), (None, 300000, 0)):
+        if segp is None:
+            monkeypatch.delenv("MWF_B200_TILE_SEGP", raising=False)
+        else:
+            monkeypatch.setenv("MWF_B200_TILE_SEGP", str(segp))
+        monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", str(cap))
+        monkeypatch.setenv("MWF_B200_TILE_WAVE", str(wave))
+        for kw, w in zip(modes, want):
+            assert mw.wfa_exact_batch(mw.opt_init(**kw), pairs) == w, (segp, cap, wave, kw)
+    # single pairs take the 1-cell-per-thread geometry
+    monkeypatch.setenv("MWF_B200_TILE_SEGP", "256")
+    monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", "0")
+    for (t, q), w in zip(pairs[3:9], want[0][3:9]):
+        assert mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR), t, q) == w
