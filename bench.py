@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--div", type=float, default=0.05)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-single", action="store_true", help="skip the single 150 kb pair leg")
+    ap.add_argument("--no-large", action="store_true", help="skip the 5 Mb pair legs (BASELINE configs 4 and 5, one pair each)")
     ap.add_argument("--cpu-threads", type=int, default=0)
     return ap.parse_args()
 
@@ -366,7 +367,35 @@ def main():
                                "value": n1 * r1[0] / (kms * 1e-3), "e2e_value": n1 * r1[0] / e2e1, "unit": UNIT,
                                "roofline_frac": r1[2] * BYTES_PER_CELL_TB / (kms * 1e-3) / 1e9 / peak,
                                "note": "one pair = one dependency chain of s scores; the tile engine cuts it into blocks of 64 scores "
-                                       "x (width/896) tiles, so only ~30-60 of the 148 SMs have work: latency-bound, not HBM-bound"}
+                                       "x (width/384) tiles of 512 threads, at most ~140 tiles: latency-bound, not HBM-bound"}
+
+    # ---- 5 Mb pairs (config 4 and config 5 surrogates, one pair each), rank 0 --------------------------------------------
+    if rank == 0 and not args.no_large and not args.no_single:
+        large = {}
+        for name, p, kw, what in (("config4", 0.0097, {"flag": mw.F_CIGAR, "step": 5000},
+                                   "BASELINE config 4 surrogate: one synthetic 5 Mb pair (p=0.0097, s ~ 231 k), low-memory mode -cp5000"),
+                                  ("config5", 0.03, {"flag": mw.F_CIGAR},
+                                   "BASELINE config 5 surrogate: one synthetic 5 Mb pair (p=0.03, s ~ 711 k, 5e11 cells), high-memory "
+                                   "CIGAR; its 505 GB of traceback bytes do not fit HBM, so the engine falls back to the segmented "
+                                   "traceback (snapshots + recompute) after the all-at-once attempt runs out of arena")):
+            t, q = synth.make_pair(5000000, p, 424242)
+            oo = mw.opt_init(**kw)
+            with mw.Batch(oo, [(t, q)]) as lb:
+                lb.upload()
+                t0 = time.perf_counter()
+                lb.run()
+                lb.wait()
+                dt = time.perf_counter() - t0
+                rl = lb.fetch()[0]
+                ll = int(lb.launches)
+            assert rl[0] > 0 and mw.cigar2score(oo, rl[3]) == (rl[0], len(t), len(q))
+            large[name] = {"workload": what, "s": rl[0], "n_iter": rl[2], "n_cigar": rl[1], "seconds": dt, "gpu_launches": ll,
+                           "value": max(len(t), len(q)) * rl[0] / dt, "unit": UNIT,
+                           "check": "CIGAR re-scored with mwf_cigar2score: score == s and it consumes both sequences"}
+            del t, q
+        large["reference_published"] = "README.md:98-99 (Xeon 6230, 1 thread): MHC (s = 229 868) 385 s high-memory / 544 s low-memory"
+        line["large_pairs"] = large
+        mw.lib().mwf_b200_release_cache()
 
     # ---- cpu_baseline: rank 0 at N=1 only ---------------------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
