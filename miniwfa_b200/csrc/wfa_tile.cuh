@@ -238,7 +238,11 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			else wflo = nl, wfhi = nh;
 		}
 	}
-	if (threadIdx.x != 0) return;
+	__shared__ long long sh_row[2];
+	__shared__ int sh_emit[4]; /* items base, n_tiles, first score of the rows, number of rows */
+	if (threadIdx.x == 0) sh_emit[1] = 0, sh_emit[3] = 0;
+	__syncthreads();
+	if (threadIdx.x == 0) {
 	if (status == TS_RUN && s > P.s_limit) status = TS_SHRINK; /* cannot happen: the all-gap alignment costs less */
 	if (status == TS_RUN && P.s_stop && s >= P.s_stop[slot]) status = TS_SEGEND; /* end of a traceback segment */
 	if (status == TS_RUN) { /* cut the next block */
@@ -269,8 +273,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			const unsigned long long base = atomicAdd(P.arena_used, (unsigned long long)(rowsize * Tb));
 			if ((long long)base + rowsize * Tb > P.arena_cap || s + Tb >= P.rowtab_stride) status = TS_ARENA;
 			else {
-				long long *rt = P.rowtab + (size_t)slot * P.rowtab_stride;
-				for (int t = 1; t <= Tb; ++t) rt[s + t] = (long long)base + (long long)(t - 1) * rowsize - A4;
+				sh_row[0] = (long long)base - A4, sh_row[1] = rowsize, sh_emit[2] = s, sh_emit[3] = Tb; /* the table is filled below, by all threads */
 				c->row_base = (long long)base - A4, c->row_size = rowsize;
 			}
 		}
@@ -292,21 +295,26 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			c->wflo = wflo, c->wfhi = wfhi, c->sid = sid;
 			c->Tb = Tb, c->A4 = A4, c->total4 = total4, c->n_tiles = n_tiles;
 			c->done_t = 0x7fffffff, c->done_last = 0;
-			const unsigned int base = atomicAdd(&P.cnt[it & 1].n_items, (unsigned int)n_tiles);
-			for (int j = 0; j < n_tiles; ++j) P.items[base + j] = make_int2(slot, j);
+			sh_emit[0] = (int)atomicAdd(&P.cnt[it & 1].n_items, (unsigned int)n_tiles), sh_emit[1] = n_tiles;
 		}
 	}
 	if (status != TS_RUN) {
 		c->status = status;
 		atomicSub(P.n_running, 1);
-		if (status == TS_SEGEND) return; /* the result record belongs to the pass that reaches the end */
-		PairOut o;
-		o.s = status == TS_DONE ? c->s : -1;
-		o.n_cigar = 0, o.n_iter = c->n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap;
-		o.status = status == TS_DONE ? ST_OK : status == TS_STOPPED ? ST_STOPPED : status == TS_ARENA ? ST_ARENA : ST_SHRINK;
-		o.pad_ = 0;
-		P.outs[pi] = o;
+		if (status != TS_SEGEND) { /* (a segment's end leaves the result record to the pass that reaches the end) */
+			PairOut o;
+			o.s = status == TS_DONE ? c->s : -1;
+			o.n_cigar = 0, o.n_iter = c->n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap;
+			o.status = status == TS_DONE ? ST_OK : status == TS_STOPPED ? ST_STOPPED : status == TS_ARENA ? ST_ARENA : ST_SHRINK;
+			o.pad_ = 0;
+			P.outs[pi] = o;
+		}
 	}
+	} /* thread 0 */
+	__syncthreads();
+	for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) P.items[sh_emit[0] + j] = make_int2(slot, j); /* the block's tiles */
+	if (threadIdx.x < sh_emit[3]) /* wf_tb_add (:33-44): where the traceback row of every score of the block starts */
+		P.rowtab[(size_t)slot * P.rowtab_stride + sh_emit[2] + 1 + threadIdx.x] = sh_row[0] + (long long)threadIdx.x * sh_row[1];
 }
 
 /* ------------------------------------------------------------------------------------------ */
