@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in C_SOURCES + CU_SOURCES]
     hdrs = [os.path.join(INC, h) for h in os.listdir(INC)]
     cli_src = os.path.join(CSRC, "main.c")
-    deps = srcs + hdrs + [os.path.abspath(__file__)]
+    deps = srcs + hdrs + [os.path.abspath(__file__)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     if not force and _newer(OUT, deps) and (not os.path.exists(cli_src) or _newer(CLI, [cli_src, OUT])):
         return OUT
     os.makedirs(OBJ, exist_ok=True)

@@ -993,7 +993,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		cw += (size_t)p.cigar_cap;
 		max_len = std::max(max_len, (long long)tl[i] + ql[i]);
 		long long sb = gap_cost(opt, tl[i]) + gap_cost(opt, ql[i]);
-		if (opt->max_s > 0) sb = std::min(sb, (long long)opt->max_s + 1);
+		if (opt->max_s > 0 && !seg) sb = std::min(sb, (long long)opt->max_s + 1); /* (pass 1 of low-memory mode has no stop tests) */
 		max_sbound = std::max(max_sbound, sb);
 		b->order[i] = i;
 	}
@@ -1177,8 +1177,10 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
 /* one pass of the tile engine over a wave of pairs: score 0, then plan + tile kernels per time block until every pair has ended.
  * The number of running pairs and of tiles per launch is read back one chunk of launches behind, so the device never waits for
  * the host; the tile count picks the geometry of the next chunk. */
-static void tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false)
+/* returns the error bits the planner raised during the pass: 1 << TS_ARENA, 1 << TS_SHRINK */
+static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false)
 {
+	int err = 0;
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
 	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
@@ -1209,10 +1211,11 @@ static void tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j 
 		if (chunk >= 1) {
 			const int *pr = b->h_running + 16 * ((chunk - 1) & 1);
 			CUDA_OK(cudaEventSynchronize(b->evc[(chunk - 1) & 1]));
-			if (pr[8] == 0) break;
+			if (pr[8] == 0) { err = pr[10]; break; }
 			if (b->n_geom > 1) g = std::max((unsigned int)pr[0], (unsigned int)pr[2]) >= many ? 1 : 0;
 		}
 	}
+	return err;
 }
 
 /* kernel parameters of the tile engine, one set per geometry */
@@ -1224,7 +1227,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.cigar = b->d_cigar;
 	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
 	P.pitch = b->pitch, P.R = b->tR;
-	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32);
+	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32), P.err = (int*)(b->d_tmisc + 40);
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
@@ -1263,11 +1266,9 @@ static bool run_tile(mwf_b200_batch_t *b)
 			/* low-memory mode (miniwfa.c:603-615).  Pass 1 of the reference only serves to find the checkpoints; here they come
 			 * from an unbanded high-memory pass (no stop tests, like mwf_wfa_seg) whose traceback bytes are walked backwards. */
 			for (int g = 0; g < 2; ++g) PP[g].seg_use = 0, PP[g].max_s = 0, PP[g].max_iter = 0;
-			tile_pass(b, PP, np);
-			CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
-			CUDA_OK(cudaStreamSynchronize(b->stream));
-			for (int i = p0; i < p0 + np; ++i)
-				if (b->h_outs[b->order[i]].status == ST_ARENA) return false; /* s^2 bytes do not fit: the caller falls back */
+			const int err = tile_pass(b, PP, np);
+			if (err & (1 << TS_SHRINK)) die("internal error: empty band after shrink");
+			if (err & (1 << TS_ARENA)) return false; /* s^2 bytes do not fit: the caller falls back */
 			wfa_tile_checkpoint_kernel<<<np, 32, 0, b->stream>>>(PP[0]);
 			CUDA_OK(cudaGetLastError());
 			++b->launches;
@@ -1290,6 +1291,7 @@ static bool run_tile(mwf_b200_batch_t *b)
 static void run_tile_segmented(mwf_b200_batch_t *b)
 {
 	const int wp = b->wave_pairs;
+	const bool lowmem = b->opt.step > 0; /* the segments are walked for checkpoints (then the banded pass 2 follows), not for the CIGAR */
 	if (b->d_snap == 0) { /* workspaces of this mode, on first use: the big arena shrinks to make room for the snapshots */
 		CUDA_OK(cudaStreamSynchronize(b->stream));
 		ws_free(b->d_arena);
@@ -1301,9 +1303,11 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		b->snapdir_stride = (int)(b->max_sbound / b->seg_P + 2);
 		const long long half = (long long)((double)free_b * 0.45) & ~255LL;
 		const long long width = b->max_len + 2LL * b->pen.nring + 2LL * TILE_TMAX + 16;
-		b->arena_total = std::min(half, ((long long)(b->seg_P + 2 * TILE_TMAX) * width * wp + 255) & ~255LL);
+		long long need = (long long)(b->seg_P + 2 * TILE_TMAX) * width * wp; /* traceback rows of one segment */
+		if (lowmem) need = half; /* ... and of pass 2, which is banded only while the reference's checkpoint matching keeps up: with
+		                            step below the penalties two snapshots can share a checkpoint and the band stops collapsing (:413-416) */
+		b->arena_total = std::min(half, (need + 255) & ~255LL);
 		b->snap_words = std::min(half, (long long)b->snapdir_stride * b->tR * width * 4 * wp) / 4;
-		if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) b->arena_total = std::max<long long>(b->arena_total, 65536);
 		ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		ws_dev(&b->d_snap, (size_t)b->snap_words * 4, b->dev);
 		ws_dev(&b->d_snapdir, sizeof(SnapDir) * (size_t)b->snapdir_stride * wp, b->dev);
@@ -1324,10 +1328,11 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		/* forward: scores only, stop tests as in mwf_wfa_core, snapshots every seg_P scores */
 		for (int g = 0; g < 2; ++g) {
 			PP[g].pair0 = p0, PP[g].n_pairs = np, PP[g].is_tb = 0, PP[g].snap_take = 1, PP[g].s_stop = 0;
-			PP[g].max_s = b->opt.max_s, PP[g].max_iter = b->opt.max_iter;
+			PP[g].max_s = lowmem ? 0 : b->opt.max_s, PP[g].max_iter = lowmem ? 0 : b->opt.max_iter; /* pass 1 has no stop tests (:569-589) */
+			PP[g].seg_use = 0;
 		}
 		CUDA_OK(cudaMemsetAsync(b->d_nsnap, 0, sizeof(int) * np, b->stream));
-		tile_pass(b, PP, np, -1, true);
+		if (tile_pass(b, PP, np, -1, true)) die("device workspace exhausted (snapshots of the segmented traceback)");
 		wfa_tile_trace_begin_kernel<<<(np + 127) / 128, 128, 0, b->stream>>>(PP[0]);
 		CUDA_OK(cudaGetLastError());
 		++b->launches;
@@ -1343,8 +1348,24 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		for (int g = 0; g < 2; ++g)
 			PP[g].is_tb = 1, PP[g].snap_take = 0, PP[g].s_stop = b->d_sstop, PP[g].max_s = 0, PP[g].max_iter = 0;
 		for (int j = max_seg; j >= 0; --j) {
-			tile_pass(b, PP, np, j, false);
-			wfa_tile_trace_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
+			if (tile_pass(b, PP, np, j, false)) die("device workspace exhausted (traceback bytes of one segment); lower MWF_B200_TILE_SEGP");
+			if (lowmem) wfa_tile_ckpt_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
+			else wfa_tile_trace_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
+			CUDA_OK(cudaGetLastError());
+			++b->launches;
+		}
+		if (lowmem && env_int("MWF_B200_DEBUG", 0)) {
+			int ns = 0, sg[16];
+			CUDA_OK(cudaStreamSynchronize(b->stream));
+			CUDA_OK(cudaMemcpy(&ns, b->d_nseg, sizeof(int), cudaMemcpyDeviceToHost));
+			CUDA_OK(cudaMemcpy(sg, b->d_seg, sizeof(int) * 16, cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[seg dbg] n_seg=%d seg0=(%d,%d) seg1=(%d,%d)\n", ns, sg[0], sg[1], sg[2], sg[3]);
+		}
+		if (lowmem) { /* pass 2: mwf_wfa_core with the checkpoints, its own (banded) traceback bytes and traceback */
+			for (int g = 0; g < 2; ++g)
+				PP[g].seg_use = 1, PP[g].s_stop = 0, PP[g].max_s = b->opt.max_s, PP[g].max_iter = b->opt.max_iter;
+			tile_pass(b, PP, np);
+			wfa_tile_traceback_kernel<<<np, 32, 0, b->stream>>>(PP[0]);
 			CUDA_OK(cudaGetLastError());
 			++b->launches;
 		}
@@ -1366,12 +1387,17 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 				for (int i = 0; i < b->n && !segmented; ++i) segmented = b->h_outs[i].status == ST_ARENA;
 			}
 			if (segmented) run_tile_segmented(b);
-		} else if (b->kernel == MWF_B200_KERNEL_TILE && !run_tile(b)) { /* low-memory request too large for a high-memory pass */
-			CUDA_OK(cudaStreamSynchronize(b->stream));
-			free_tile(b);
-			b->kernel = (b->n >= b->n_sm / 4 || b->max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
-			alloc_streaming(b);
-		}
+		} else if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb) { /* low-memory mode */
+			const bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
+			if (segmented || !run_tile(b)) { /* the unbanded pass does not fit the arena as s^2 bytes */
+				if (env_int("MWF_B200_LOWMEM_STREAMING", 0)) { /* the reference's two-stripe pass 1 on the streaming kernels */
+					CUDA_OK(cudaStreamSynchronize(b->stream));
+					free_tile(b);
+					b->kernel = (b->n >= b->n_sm / 4 || b->max_len < 32768) ? MWF_B200_KERNEL_CTA : MWF_B200_KERNEL_GRID;
+					alloc_streaming(b);
+				} else run_tile_segmented(b);
+			}
+		} else if (b->kernel == MWF_B200_KERNEL_TILE) run_tile(b);
 		if (b->kernel == MWF_B200_KERNEL_TILE) {
 		} else if (b->kernel == MWF_B200_KERNEL_CTA) {
 			launch_cta(b, make_params(b, b->n_slots), b->n_slots);

@@ -70,6 +70,7 @@ struct TParams {
 	int2 *items;
 	TileCounters *cnt;         /* [2] */
 	int *n_running;
+	int *err;                  /* bits 1 << TS_ARENA, 1 << TS_SHRINK raised by the planner */
 	uint8_t *arena;
 	long long arena_cap;
 	unsigned long long *arena_used;
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 	}
 	if (status != TS_RUN) {
 		c->status = status;
+		if (status == TS_ARENA || status == TS_SHRINK) atomicOr(P.err, 1 << status);
 		atomicSub(P.n_running, 1);
 		if (status != TS_SEGEND) { /* (a segment's end leaves the result record to the pass that reaches the end) */
 			PairOut o;
@@ -757,6 +759,7 @@ __global__ void wfa_tile_trace_begin_kernel(const TParams P)
 	t.fwd_status = c->status, t.s_final = c->s, t.i = pd.ql - 1, t.k = pd.tl - 1, t.row = c->s, t.last = 0;
 	t.cur_op = -1, t.n_out = 0, t.cur_len = 0, t.pad = 0, t.n_iter = c->n_iter;
 	P.trace[slot] = t;
+	if (P.step > 0 && P.n_seg) P.n_seg[slot] = c->status == TS_DONE ? c->s / P.step : 0; /* snapshots at m*step - 1 < final score (:585) */
 }
 
 /* start segment j of every pair that has one: segment 0 starts at score 0 (wfa_tile_init_kernel has run), segment j > 0 at
@@ -857,6 +860,57 @@ __global__ void wfa_tile_trace_seg_kernel(const TParams P, int j)
 #undef CIG_PUSH
 	if (lane == 0) {
 		t.i = i, t.k = k, t.row = row, t.last = last, t.cur_op = cur_op, t.n_out = n_out, t.cur_len = cur_len;
+		*tsp = t;
+	}
+}
+
+
+/* the checkpoint walk of wfa_tile_checkpoint_kernel over the traceback bytes of segment j only (low-memory requests whose
+ * unbanded pass does not fit the arena as s^2 bytes): stops when it needs a row at or below the segment's first score */
+__global__ void wfa_tile_ckpt_seg_kernel(const TParams P, int j)
+{
+	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot], lane = threadIdx.x & 31;
+	TraceState *tsp = P.trace + slot;
+	const int n_snap = P.n_snap[slot];
+	if (tsp->fwd_status != TS_DONE || j > n_snap) return;
+	const TileCtl *c = P.ctl + slot;
+	const PairDesc pd = P.pairs[pi];
+	const uint8_t *T8 = P.seq + pd.t_off, *Q8 = P.seq + pd.q_off;
+	const long long *rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
+	const int doff = tile_doff(P, pd.tl), s_lo = j * P.snap_P, step = P.step;
+	const Pen pen = P.pen;
+	int *seg = P.seg + (size_t)slot * P.seg_stride;
+	TraceState t = *tsp;
+	if (j == n_snap) t.last = c->last;
+	int i = t.i, k = t.k, row = t.row, last = t.last;
+	int ks = row / step - 1, snap_s = (ks + 1) * step - 1; /* checkpoints at or above `row` are already known */
+	while (row > s_lo && ks >= 0) {
+		if (last == 0) {
+			for (;;) {
+				const int ii = i - lane, kk = k - lane;
+				const bool same = ii >= 0 && kk >= 0 && Q8[ii] == T8[kk];
+				const unsigned m = __ballot_sync(0xffffffffu, !same);
+				if (m) { const int cnt = __ffs(m) - 1; i -= cnt, k -= cnt; break; }
+				i -= 32, k -= 32;
+			}
+		}
+		const int x = __ldcg(P.arena + rowtab[row] + (i - k + doff));
+		const int state = last == 0 ? (x & 7) : last;
+		const int ext = state > 0 ? (x >> (state + 2)) & 1 : 0;
+		if (state == 0) { --i, --k; row -= pen.x; }
+		else if (state == 1) { --i; row -= ext ? pen.e1 : pen.oe1; }
+		else if (state == 3) { --i; row -= ext ? pen.e2 : pen.oe2; }
+		else if (state == 2) { --k; row -= ext ? pen.e1 : pen.oe1; }
+		else { --k; row -= ext ? pen.e2 : pen.oe2; }
+		last = (state > 0 && ext) ? state : 0;
+		while (ks >= 0 && row <= snap_s) {
+			if (lane == 0) seg[2 * ks] = row, seg[2 * ks + 1] = i - k;
+			--ks, snap_s -= step;
+		}
+	}
+	if (lane == 0) {
+		t.i = i, t.k = k, t.row = row, t.last = last;
+		if (ks < 0) t.fwd_status = TS_IDLE; /* every checkpoint found: the earlier segments need no recompute */
 		*tsp = t;
 	}
 }

@@ -282,21 +282,27 @@ def test_tile_geometry_variants(monkeypatch):
                 assert b.fetch() == want[i], (cpt, nt, T, wave, kw)
 
 
-def test_lowmem_falls_back_when_the_highmem_pass_does_not_fit(monkeypatch):
-    """Low-memory requests run on the tile engine through a high-memory pass; when its s^2 traceback bytes do not fit the
-    arena the batch is rerun on the streaming two-stripe kernels.  Same bits either way."""
+def test_lowmem_when_the_highmem_pass_does_not_fit(monkeypatch):
+    """Low-memory requests run on the tile engine through an unbanded high-memory pass; when its s^2 traceback bytes do not
+    fit the arena the checkpoints come from the segmented walk (snapshots + recompute), or, on request, from the reference's
+    two-stripe pass 1 on the streaming kernels.  Same bits every way."""
     mw.set_kernel(mw.KERNEL_TILE)
     pairs = synth.make_batch(3, 6000, 0.08, 4242)
-    kw = {"flag": mw.F_CIGAR, "step": 300}
-    want = [orc.checker_exact(orc.make_opt(**kw), t, q) for t, q in pairs]
-    for cap in (0, 200000):
-        monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", str(cap))
-        with mw.Batch(mw.opt_init(**kw), pairs) as b:
-            assert b.kernel_used == mw.KERNEL_TILE
-            b.upload()
-            b.run()
-            assert b.fetch() == want, cap
-            assert (b.kernel_used == mw.KERNEL_TILE) == (cap == 0)
+    for kw in ({"flag": mw.F_CIGAR, "step": 300}, {"flag": mw.F_CIGAR, "step": 37, "max_s": 1500}, {"flag": mw.F_CIGAR, "step": 5000}):
+        want = [orc.checker_exact(orc.make_opt(**kw), t, q) for t, q in pairs]
+        for cap, streaming, segp in ((0, 0, None), (200000, 0, None), (200000, 1, None), (0, 0, 256), (0, 0, 1024)):
+            monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", str(cap))
+            monkeypatch.setenv("MWF_B200_LOWMEM_STREAMING", str(streaming))
+            if segp is None:
+                monkeypatch.delenv("MWF_B200_TILE_SEGP", raising=False)
+            else:
+                monkeypatch.setenv("MWF_B200_TILE_SEGP", str(segp))
+            with mw.Batch(mw.opt_init(**kw), pairs) as b:
+                assert b.kernel_used == mw.KERNEL_TILE
+                b.upload()
+                b.run()
+                assert b.fetch() == want, (kw, cap, streaming, segp)
+                assert (b.kernel_used == mw.KERNEL_TILE) == (not (cap and streaming))
 
 
 def test_segmented_traceback(monkeypatch):

@@ -10,7 +10,7 @@ from oracle import orc
 seed, n_cases = int(sys.argv[1]), int(sys.argv[2])
 max_len = int(sys.argv[3]) if len(sys.argv) > 3 else 6000
 rng = random.Random(seed)
-ENV = ["MWF_B200_TILE_CPT", "MWF_B200_TILE_THREADS", "MWF_B200_TILE_T", "MWF_B200_TILE_SEGP", "MWF_B200_TILE_WAVE", "MWF_B200_TILE_ARENA_MAX", "MWF_B200_TILE_SWITCH"]
+ENV = ["MWF_B200_TILE_CPT", "MWF_B200_TILE_THREADS", "MWF_B200_TILE_T", "MWF_B200_TILE_SEGP", "MWF_B200_TILE_WAVE", "MWF_B200_TILE_ARENA_MAX", "MWF_B200_TILE_SWITCH", "MWF_B200_LOWMEM_STREAMING"]
 
 
 def mutate(t, p):
@@ -82,6 +82,8 @@ for case in range(n_cases):
         env.update(MWF_B200_TILE_ARENA_MAX=rng.choice([70000, 300000, 2000000]))
     if rng.random() < 0.3:
         env.update(MWF_B200_TILE_WAVE=rng.randint(1, 4))
+    if rng.random() < 0.15:
+        env.update(MWF_B200_LOWMEM_STREAMING=1)
     for k, v in env.items():
         os.environ[k] = str(v)
     kw = rand_opt()
@@ -92,6 +94,12 @@ for case in range(n_cases):
         pairs = [(t[:400], q[:400]) for t, q in pairs]
     if not pairs:
         continue
+    if os.environ.get("FUZZ_ONLY") and case != int(os.environ["FUZZ_ONLY"]):
+        continue
+    if case < int(os.environ.get("FUZZ_FROM", "0")):
+        continue
+    if os.environ.get("FUZZ_V"):
+        print("case", case, "fam", fam, "env", env, "opt", kw, "lens", [(len(t), len(q)) for t, q in pairs][:6], flush=True)
     if any(len(set(t + q)) >= 255 for t, q in pairs):  # the reference needs two unused byte values (miniwfa.c:189-201)
         want = [orc.oracle_exact(orc.make_opt(**kw), t, q) for t, q in pairs]
     else:
@@ -101,6 +109,8 @@ for case in range(n_cases):
         bad += 1
         for i, (g, w) in enumerate(zip(got, want)):
             if g != w:
+                if os.environ.get("FUZZ_DUMP"):
+                    open(os.environ["FUZZ_DUMP"], "wb").write(len(pairs[i][0]).to_bytes(4, "little") + pairs[i][0] + pairs[i][1])
                 print("MISMATCH case", case, "pair", i, "lens", len(pairs[i][0]), len(pairs[i][1]), "fam", fam, "env", env, "opt", kw,
                       "want", w[:3], "got", g[:3], flush=True)
                 break
