@@ -11,7 +11,8 @@
  *                           once, 16-byte aligned with zeroed slack, into HBM.  No sentinel
  *                           bytes are needed (the kernel clamps the match run to the matrix),
  *                           so inputs using all 256 byte values are accepted.
- *   mwf_b200_batch_run      the whole of mwf_wfa_core's score loop (:397-426) -- the extend
+ *   mwf_b200_batch_run      (tile engine: wfa_tile.cuh; streaming kernels: wfa_engine.cu)
+ *                           the whole of mwf_wfa_core's score loop (:397-426) -- the extend
  *                           loop + wf_extend1_padded (:400-411, :212-226), wf_next_basic /
  *                           wf_next_prep / wf_next_score / wf_next_tb (:243-327),
  *                           wf_stripe_shrink (:144-171), the checkpoint band collapse
@@ -64,7 +65,9 @@ mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t n_pairs, c
 /* run on this CUDA stream (a cudaStream_t) instead of the batch's own */
 void mwf_b200_batch_set_stream(mwf_b200_batch_t *b, void *cuda_stream);
 void mwf_b200_batch_upload(mwf_b200_batch_t *b, const char *const *ts, const char *const *qs); /* host -> pinned -> HBM, async */
-void mwf_b200_batch_run(mwf_b200_batch_t *b);     /* enqueue the alignment kernels, async */
+void mwf_b200_batch_run(mwf_b200_batch_t *b);     /* run the alignment kernels; returns once every launch is enqueued (the tile engine's
+                                                      host loop launches one plan + one tile kernel per block of scores and reads the
+                                                      number of running pairs back one chunk behind, so it returns near the end) */
 void mwf_b200_batch_wait(mwf_b200_batch_t *b);    /* block until the stream is idle; aborts on a device-side error */
 void mwf_b200_batch_fetch(mwf_b200_batch_t *b, void *km, mwf_rst_t *r); /* HBM -> host; r[0..n_pairs) */
 void mwf_b200_batch_destroy(mwf_b200_batch_t *b);

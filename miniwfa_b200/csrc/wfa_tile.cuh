@@ -499,6 +499,101 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 	return myfl;
 }
 
+/* split-phase step barrier: a warp arrives when its stores of a score are done and waits only where it first needs another
+ * warp's cells -- the d-1 / d+1 neighbours of its outermost diagonals -- so most of the next score overlaps the wait */
+__device__ __forceinline__ void step_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+/* the interior step (EDGE = false) for 4 cells per thread, reordered around the split-phase barrier:
+ *   loads of the own columns, cells 1 and 2 of every thread and their sequence probes  -- need nothing from other warps
+ *   wait(previous score of all warps)
+ *   neighbour columns of lanes 0 / 31, cells 0 and 3, then all stores                  -- stores only now: the ring slots they
+ *                                                                                         overwrite were still being read
+ * Same arithmetic as tile_cells<MODE, false, 4>. */
+template<int MODE>
+__device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, const int4 &q1, const int4 &q2, int d0,
+                                                   const int (&kmin)[4], const int (&kspan)[4],
+                                                   const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
+                                                   bool no_left, bool no_right, uint64_t *stepbar, bool wait, uint32_t parity, CellOut<4> &o)
+{
+	const int lane = threadIdx.x & 31;
+	int ho1[4], pe1[4], pf1[4], ho2[4], pe2[4], pf2[4], hx[4];
+	ldsv<4>(sb + qh.y, ho1); ldsv<4>(sb + q1.x, pe1); ldsv<4>(sb + q1.y, pf1); ldsv<4>(sb + qh.z, ho2);
+	ldsv<4>(sb + q2.x, pe2); ldsv<4>(sb + q2.y, pf2); ldsv<4>(sb + qh.x, hx);
+	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		A1[j + 1] = max(ho1[j], pe1[j]), A2[j + 1] = max(ho2[j], pe2[j]);
+		C1[j + 1] = max(ho1[j], pf1[j]), C2[j + 1] = max(ho2[j], pf2[j]);
+		if (MODE != MODE_SCORE) bA1[j + 1] = ho1[j] < pe1[j], bA2[j + 1] = ho2[j] < pe2[j], bC1[j + 1] = ho1[j] < pf1[j], bC2[j + 1] = ho2[j] < pf2[j];
+	}
+	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
+	A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
+	C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+	C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	if (MODE != MODE_SCORE) {
+		const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
+		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+	}
+	int h0[4];
+	bool ext[4];
+	uint32_t px[4], tbw = 0;
+#define TILE_CELL(j) do { \
+		const int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2] + 1, F2 = C2[j + 2] + 1; \
+		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = hx[j] + 1; \
+		const int H = max(hxp, gmx); \
+		if (MODE != MODE_SCORE) { \
+			const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4)); \
+			tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j); \
+		} \
+		o.E1[j] = E1, o.E2[j] = E2, o.F1[j] = F1, o.F2[j] = F2, h0[j] = H; \
+		ext[j] = (unsigned)(H - kmin[j]) <= (unsigned)kspan[j]; \
+		const int tp = ext[j] ? H + 1 : 0, qp = ext[j] ? d0 + j + H + 1 : 0; \
+		px[j] = seq4(T, tp) ^ seq4(Q, qp); \
+	} while (0)
+	TILE_CELL(1);
+	TILE_CELL(2);
+	if (wait) mbar_wait(stepbar, parity); /* every warp has finished the previous score */
+	{
+		const bool left = lane == 0, edge_lane = (left && !no_left) || (lane == 31 && !no_right);
+		const uint32_t nb = sb + (left ? -4 : 16);
+		const int o1 = lds1_if(nb + qh.y, edge_lane), o2 = lds1_if(nb + qh.z, edge_lane);
+		const int x1 = lds1_if(nb + (left ? q1.x : q1.y), edge_lane), x2 = lds1_if(nb + (left ? q2.x : q2.y), edge_lane);
+		const int m1 = max(o1, x1), m2 = max(o2, x2);
+		if (lane == 0) A1[0] = m1, A2[0] = m2;
+		if (lane == 31) C1[5] = m1, C2[5] = m2;
+		if (MODE != MODE_SCORE) {
+			if (lane == 0) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
+			if (lane == 31) bC1[5] = o1 < x1, bC2[5] = o2 < x2;
+		}
+	}
+	TILE_CELL(0);
+	TILE_CELL(3);
+#undef TILE_CELL
+	stsv<4>(sb + q1.z, o.E1); stsv<4>(sb + q1.w, o.F1); stsv<4>(sb + q2.z, o.E2); stsv<4>(sb + q2.w, o.F2);
+	bool more = false;
+	bool unres[4];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int kmax = kmin[j] + kspan[j];
+		const int adv = __clz(__brev(px[j])) >> 3;
+		const int k = min(h0[j] + adv, kmax);
+		unres[j] = ext[j] && px[j] == 0 && k < kmax;
+		more |= unres[j];
+		o.H[j] = ext[j] ? k : h0[j];
+	}
+	if (more) {
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (unres[j]) o.H[j] = tile_extend_more(T, Q, o.H[j], d0 + j, kmin[j] + kspan[j]);
+	}
+	stsv<4>(sb + qh.w, o.H);
+	o.tb = tbw;
+}
+
 __device__ __forceinline__ bool on_matrix_u(int d, int k, int tl, int ql)
 {
 	return (unsigned)(k + 1) <= (unsigned)tl && (unsigned)(d + k + 1) <= (unsigned)ql;
@@ -538,14 +633,14 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
 	int32_t *rows = smem_tile;
 	int *sc = rows + (size_t)R * W;                          /* [0..2] flags, [3] item */
-	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8);
+	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8), *stepbar = reinterpret_cast<uint64_t*>(sc + 10);
 	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
 	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
 	const unsigned int n_items = P.cnt[it & 1].n_items;
 	const uint32_t sb = smem_u32(rows) + 4 * CPT * tid;
 	const bool no_left = tid == 0, no_right = tid == NT - 1;
-	if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-	uint32_t phase = 0;
+	if (tid == 0) { mbar_init(bar, 1); mbar_init(stepbar, NT >> 5); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	uint32_t phase = 0, step_phase = 0;
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) sc[3] = (int)atomicAdd(&P.cnt[it & 1].next, 1u);
@@ -609,7 +704,24 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 		}
 		/* ---- Tb fused next+extend steps ---- */
 		CellOut<CPT> o;
-		if (!special) {
+		bool stepped = false;
+		if constexpr (CPT == 4) {
+			if (!special) { /* interior tile, throughput geometry: split-phase step barrier */
+				for (int t = 1; t <= Tb; ++t) {
+					hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
+					const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
+					tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, T, Q, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
+					if (t > 1) ++step_phase;
+					if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
+					if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
+					if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); }
+				}
+				__syncthreads();
+				stepped = true;
+			}
+		}
+		if (stepped) {
+		} else if (!special) {
 			for (int t = 1; t <= Tb; ++t) {
 				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
 				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
