@@ -961,9 +961,9 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	mwf_b200_batch_t *b = new mwf_b200_batch_t();
 	b->dev = mwf_b200_get_device();
 	CUDA_OK(cudaSetDevice(b->dev));
-	cudaDeviceProp prop;
-	CUDA_OK(cudaGetDeviceProperties(&prop, b->dev));
-	b->n_sm = prop.multiProcessorCount;
+	int smem_optin = 0; /* (cudaGetDeviceProperties costs tens of milliseconds; two attributes are all that is needed) */
+	CUDA_OK(cudaDeviceGetAttribute(&b->n_sm, cudaDevAttrMultiProcessorCount, b->dev));
+	CUDA_OK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->dev));
 	b->opt = *opt;
 	b->n = n_pairs;
 	b->is_tb = !!(opt->flag & MWF_F_CIGAR);
@@ -1027,7 +1027,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		G.W = G.CPT * G.NT;
 		G.smem = (size_t)b->tR * G.W * 4 + 64;
 		G.fn = 0, G.fn_score = 0, G.grid = 0;
-		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)prop.sharedMemPerBlockOptin &&
+		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)smem_optin &&
 			(G.W - 2 * G.HL) / 2 - 4 >= 2 * G.HL + n + 8;
 	}
 	int umax = b->geom[0].W - 2 * b->geom[0].HL, wmax = b->geom[0].W;
