@@ -92,6 +92,8 @@ for case in range(n_cases):
     pairs = [(t, q) for t, q in pairs if not (len(t) + len(q) == 0 and kw.get("flag"))]
     if kw.get("step") == 1:
         pairs = [(t[:400], q[:400]) for t, q in pairs]
+    elif 0 < kw.get("step", 0) < 64:  # the reference keeps a snapshot of the whole ring every `step` scores: host memory
+        pairs = [(t[:6000], q[:6000]) for t, q in pairs]
     if not pairs:
         continue
     if os.environ.get("FUZZ_ONLY") and case != int(os.environ["FUZZ_ONLY"]):
