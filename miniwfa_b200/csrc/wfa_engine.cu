@@ -846,6 +846,30 @@ static void ws_free(void *p)
 template<class T> static bool ws_dev(T **out, size_t bytes, int dev) { return ws_alloc((void**)out, bytes, false, dev); }
 template<class T> static bool ws_host(T **out, size_t bytes) { return ws_alloc((void**)out, bytes, true, 0); }
 
+/* an "as much as is free" buffer (the traceback arena when the worst case exceeds the budget): any cached device buffer of at
+ * least min_bytes will do -- the free memory differs a little from call to call, and missing the cache by a few MB would mean
+ * freeing and reallocating >100 GB.  Returns the size actually obtained. */
+static long long ws_dev_flex(uint8_t **out, long long want, long long min_bytes, int dev)
+{
+	{
+		std::lock_guard<std::mutex> lk(g_ws_mu);
+		int best = -1;
+		for (size_t i = 0; i < g_ws_free.size(); ++i) {
+			const WsEntry &e = g_ws_free[i];
+			if (!e.host && e.dev == dev && (long long)e.bytes >= min_bytes && (best < 0 || e.bytes > g_ws_free[best].bytes)) best = (int)i;
+		}
+		if (best >= 0) {
+			const WsEntry e = g_ws_free[best];
+			g_ws_free.erase(g_ws_free.begin() + best);
+			g_ws_live[e.p] = e;
+			*out = (uint8_t*)e.p;
+			return (long long)e.bytes;
+		}
+	}
+	ws_dev(out, (size_t)want, dev);
+	return want;
+}
+
 struct mwf_b200_batch {
 	int dev, kernel, n, n_sm, threads, n_slots;
 	mwf_opt_t opt;
@@ -876,7 +900,7 @@ struct mwf_b200_batch {
 	/* tile engine (wfa_tile.cuh) */
 	struct TileGeom { int CPT, NT, T, HL, W, grid; size_t smem; tile_kernel_fn fn, fn_score; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
 	int n_geom, tR, wave_pairs, s_limit;
-	long long max_len, max_sbound;
+	long long max_len, max_sbound, arena_full; /* arena_full: the arena when everything that is free is taken */
 	int *d_nseg;
 	/* segmented traceback */
 	int seg_P;
@@ -1001,7 +1025,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
 	b->seq_bytes = off + 64, b->cigar_words = cw;
 	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
-	b->max_len = max_len, b->max_sbound = max_sbound, b->d_nseg = 0;
+	b->max_len = max_len, b->max_sbound = max_sbound, b->arena_full = 0, b->d_nseg = 0;
 	b->seg_P = 0, b->d_snap = 0, b->snap_words = 0, b->d_snapdir = 0, b->snapdir_stride = 0, b->d_nsnap = 0, b->d_sstop = 0, b->h_nsnap = 0, b->d_trace = 0;
 
 	/* kernel family */
@@ -1092,8 +1116,17 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			const long long budget = (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0);
 			long long worst = (max_sbound + 2) * (max_len + 2LL * n + 2LL * TILE_TMAX + 16);
 			worst = std::max((worst + 255) & ~255LL, 65536LL);
-			b->arena_total = (long long)std::min((double)budget, (double)worst * wp) & ~255LL;
-			if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) b->arena_total = std::min<long long>(b->arena_total, env_int("MWF_B200_TILE_ARENA_MAX", 0)); /* tests */
+			b->arena_full = (long long)std::min((double)budget, (double)worst * wp) & ~255LL;
+			/* first try: what pairs of up to ~6 % divergence need (s ~ 0.3 n, s^2 bytes); a batch that needs more is rerun with all
+			 * that is free, and beyond that with the segmented traceback.  Asking for 150 GB up front costs seconds in cudaMalloc. */
+			double expect = 0;
+			for (int i = 0; i < std::min(wp, n_pairs); ++i) {
+				const double len = std::max(tl[b->order[i]], ql[b->order[i]]);
+				expect += 0.09 * len * len + 4096.0 * len;
+			}
+			b->arena_total = (long long)std::min((double)b->arena_full, std::max(expect, 64.0 * 1048576)) & ~255LL;
+			if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) /* tests */
+				b->arena_total = b->arena_full = std::min<long long>(b->arena_total, env_int("MWF_B200_TILE_ARENA_MAX", 0));
 			if (b->arena_total < 4096) die("not enough free device memory for the traceback arena");
 			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		}
@@ -1274,7 +1307,9 @@ static bool run_tile(mwf_b200_batch_t *b)
 			++b->launches;
 			for (int g = 0; g < 2; ++g) PP[g].seg_use = 1, PP[g].max_s = b->opt.max_s, PP[g].max_iter = b->opt.max_iter; /* pass 2: mwf_wfa_core with the checkpoints */
 		}
-		tile_pass(b, PP, np);
+		const int err2 = tile_pass(b, PP, np);
+		if (err2 & (1 << TS_SHRINK)) die("internal error: empty band after shrink");
+		if ((err2 & (1 << TS_ARENA)) && b->is_tb) return false; /* the caller grows the arena, or goes segmented */
 		if (b->is_tb) {
 			wfa_tile_traceback_kernel<<<np, 32, 0, b->stream>>>(PP[0]);
 			CUDA_OK(cudaGetLastError());
@@ -1372,6 +1407,18 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 	}
 }
 
+/* the first, expected-size arena was too small: take all that is free (false when that is what we already have) */
+static bool grow_arena(mwf_b200_batch_t *b)
+{
+	if (b->arena_total >= b->arena_full) return false;
+	CUDA_OK(cudaStreamSynchronize(b->stream));
+	ws_free(b->d_arena);
+	b->d_arena = 0;
+	b->arena_total = ws_dev_flex(&b->d_arena, b->arena_full, b->arena_full / 2, b->dev) & ~255LL;
+	b->arena_full = b->arena_total;
+	return true;
+}
+
 extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 {
 	CUDA_OK(cudaSetDevice(b->dev));
@@ -1380,16 +1427,16 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 	if (b->n > 0) {
 		if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb && b->opt.step <= 0) { /* high-memory CIGAR */
 			bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
-			if (!segmented) { /* optimistic: all s^2 traceback bytes at once */
-				run_tile(b);
-				CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
-				CUDA_OK(cudaStreamSynchronize(b->stream));
-				for (int i = 0; i < b->n && !segmented; ++i) segmented = b->h_outs[i].status == ST_ARENA;
+			while (!segmented) { /* optimistic: all s^2 traceback bytes at once */
+				if (run_tile(b)) break;
+				if (!grow_arena(b)) segmented = true;
 			}
 			if (segmented) run_tile_segmented(b);
 		} else if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb) { /* low-memory mode */
-			const bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
-			if (segmented || !run_tile(b)) { /* the unbanded pass does not fit the arena as s^2 bytes */
+			bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
+			while (!segmented && !run_tile(b)) /* the unbanded pass does not fit the arena as s^2 bytes */
+				if (!grow_arena(b)) segmented = true;
+			if (segmented) {
 				if (env_int("MWF_B200_LOWMEM_STREAMING", 0)) { /* the reference's two-stripe pass 1 on the streaming kernels */
 					CUDA_OK(cudaStreamSynchronize(b->stream));
 					free_tile(b);
