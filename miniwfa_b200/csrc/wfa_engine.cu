@@ -902,6 +902,8 @@ struct mwf_b200_batch {
 	int n_geom, tR, wave_pairs, s_limit;
 	long long max_len, max_sbound, arena_full; /* arena_full: the arena when everything that is free is taken */
 	int *d_nseg;
+	uint32_t *d_seqp; /* two-bit packed sequences */
+	int *d_packed;
 	/* segmented traceback */
 	int seg_P;
 	int32_t *d_snap;
@@ -1025,7 +1027,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
 	b->seq_bytes = off + 64, b->cigar_words = cw;
 	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
-	b->max_len = max_len, b->max_sbound = max_sbound, b->arena_full = 0, b->d_nseg = 0;
+	b->max_len = max_len, b->max_sbound = max_sbound, b->arena_full = 0, b->d_nseg = 0, b->d_seqp = 0, b->d_packed = 0;
 	b->seg_P = 0, b->d_snap = 0, b->snap_words = 0, b->d_snapdir = 0, b->snapdir_stride = 0, b->d_nsnap = 0, b->d_sstop = 0, b->h_nsnap = 0, b->d_trace = 0;
 
 	/* kernel family */
@@ -1101,6 +1103,10 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		b->items_cap = (size_t)wp * ((size_t)b->pitch / umax + 2);
 		ws_dev(&b->d_items, sizeof(int2) * b->items_cap, b->dev);
 		ws_dev(&b->d_tmisc, 128, b->dev);
+		if (env_int("MWF_B200_TILE_PACK", 1)) {
+			ws_dev(&b->d_seqp, b->seq_bytes / 4 + 256, b->dev);
+			ws_dev(&b->d_packed, sizeof(int) * std::max(1, n_pairs), b->dev);
+		}
 		ws_host(&b->h_running, 2 * 64);
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
@@ -1164,6 +1170,10 @@ extern "C" void mwf_b200_batch_upload(mwf_b200_batch_t *b, const char *const *ts
 	CUDA_OK(cudaMemcpyAsync(b->d_pairs, b->pairs.data(), sizeof(PairDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
 	CUDA_OK(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int) * b->n, cudaMemcpyHostToDevice, b->stream));
 	b->h2d = (int64_t)b->seq_bytes + (int64_t)(sizeof(PairDesc) + sizeof(int)) * b->n;
+	if (b->d_seqp && b->n > 0) { /* two-bit copies for the tile engine's match-run probes */
+		wfa_pack2_kernel<<<b->n, 256, 0, b->stream>>>(b->d_seq, b->d_pairs, b->d_seqp, b->d_packed);
+		CUDA_OK(cudaGetLastError());
+	}
 }
 
 static KParams make_params(const mwf_b200_batch_t *b, int n_slots)
@@ -1257,7 +1267,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	TParams P;
 	memset(&P, 0, sizeof(P));
 	P.pen = b->pen, P.is_tb = b->is_tb, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter;
-	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.cigar = b->d_cigar;
+	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.seqp = b->d_seqp, P.packed = b->d_packed, P.cigar = b->d_cigar;
 	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
 	P.pitch = b->pitch, P.R = b->tR;
 	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32), P.err = (int*)(b->d_tmisc + 40);
@@ -1525,6 +1535,7 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
 	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
 	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_seqp); ws_free(b->d_packed);
 	ws_free(b->d_snap); ws_free(b->d_snapdir); ws_free(b->d_nsnap); ws_free(b->d_sstop); ws_free(b->h_nsnap); ws_free(b->d_trace);
 	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
 	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);

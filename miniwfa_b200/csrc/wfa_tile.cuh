@@ -62,6 +62,8 @@ struct TParams {
 	const PairDesc *pairs;
 	PairOut *outs;
 	const uint8_t *seq;
+	const uint32_t *seqp;      /* two-bit packed copies (wfa_pack2_kernel), word offset = raw byte offset / 16 */
+	const int *packed;         /* [pair index]: 1 when the pair was packed */
 	uint32_t *cigar;
 	TileCtl *ctl;              /* [n_pairs] */
 	int32_t *state;            /* [n_pairs][2][R][pitch] */
@@ -358,32 +360,45 @@ __device__ __forceinline__ int lds1_if(uint32_t a, bool p) /* NEG_INF unless p; 
 	return v;
 }
 
-/* 4 bytes of a sequence starting at byte `pos` (the funnel shift takes its amount modulo 32) */
-__device__ __forceinline__ uint32_t seq4(const uint32_t *__restrict__ w, int pos)
-{
-	const uint32_t *p = w + (pos >> 2);
-	return __funnelshift_r(__ldg(p), __ldg(p + 1), pos << 3);
-}
+/*
+ * The two sequences of a pair as the match-run probe sees them (wf_extend1_padded, miniwfa.c:212-226): 32-bit words holding
+ * either 4 bytes (raw) or, when the pair uses at most 4 distinct byte values, 16 two-bit codes (wfa_pack2_kernel).  Equal
+ * codes <=> equal bytes, so the run lengths are the same; the packed form touches 4x fewer cache lines per probe (the kernel is
+ * bound by the L1 data pipe) and one probe covers 16 bases, so the "longer than one probe" path is left to the optimal path.
+ * The three shift amounts make one code path serve both forms.
+ */
+struct SeqView {
+	const uint32_t *T, *Q;
+	int s_idx, s_amt, s_adv; /* position -> word index (>> 2 | 4), funnel amount (<< 3 | 1), differing bit -> position (>> 3 | 1) */
+	__device__ __forceinline__ uint32_t word(const uint32_t *__restrict__ w, int pos) const
+	{
+		const uint32_t *p = w + (pos >> s_idx);
+		return __funnelshift_r(__ldg(p), __ldg(p + 1), pos << s_amt); /* the funnel shift takes its amount modulo 32 */
+	}
+	__device__ __forceinline__ uint32_t probe(int tp, int qp) const { return word(T, tp) ^ word(Q, qp); }
+	__device__ __forceinline__ int advance(uint32_t x) const { return __clz(__brev(x)) >> s_adv; } /* all positions of the word when x == 0 */
+};
 
-/* continue a match run: everything up to k is known to match (wf_extend1_padded, miniwfa.c:212-226), clamped to kmax.
- * 16 bytes of each sequence per round, all ten loads in flight together: on the optimal path a run is ~1/divergence bases long
- * and this loop is the serial part of a score step. */
-__device__ __noinline__ int tile_extend_more(const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q, int k, int d, int kmax)
+/* continue a match run: everything up to k is known to match, clamped to kmax.  Four words of each sequence per round (16 bytes
+ * or 64 packed bases), all ten loads in flight together: on the optimal path a run is ~1/divergence bases long and this loop is
+ * the serial part of a score step. */
+__device__ __noinline__ int tile_extend_more(const SeqView sv, int k, int d, int kmax)
 {
+	const int ppw = 32 >> sv.s_adv; /* positions per word */
 	while (k < kmax) {
 		const int tp = k + 1, qp = d + k + 1;
-		const uint32_t *tw = T + (tp >> 2), *qw = Q + (qp >> 2);
+		const uint32_t *tw = sv.T + (tp >> sv.s_idx), *qw = sv.Q + (qp >> sv.s_idx);
 		uint32_t a[5], b[5];
 #pragma unroll
 		for (int i = 0; i < 5; ++i) a[i] = __ldg(tw + i), b[i] = __ldg(qw + i);
-		int adv = 16;
+		int adv = 4 * ppw;
 #pragma unroll
 		for (int i = 3; i >= 0; --i) {
-			const uint32_t x = __funnelshift_r(a[i], a[i + 1], tp << 3) ^ __funnelshift_r(b[i], b[i + 1], qp << 3);
-			if (x) adv = 4 * i + ((__ffs(x) - 1) >> 3);
+			const uint32_t x = __funnelshift_r(a[i], a[i + 1], tp << sv.s_amt) ^ __funnelshift_r(b[i], b[i + 1], qp << sv.s_amt);
+			if (x) adv = i * ppw + ((__ffs(x) - 1) >> sv.s_adv);
 		}
 		k += adv;
-		if (adv < 16) break;
+		if (adv < 4 * ppw) break;
 	}
 	return min(k, kmax);
 }
@@ -400,7 +415,7 @@ template<int CPT> struct CellOut { int H[CPT], E1[CPT], F1[CPT], E2[CPT], F2[CPT
 template<int MODE, bool EDGE, int CPT>
 __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int4 &q1, const int4 &q2, int d0, int lo_t, int hi_t, int dfin, int tl,
                                           const int (&kmin)[CPT], const int (&kspan)[CPT],
-                                          const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
+                                          const SeqView &sv,
                                           bool no_left, bool no_right, bool useful, CellOut<CPT> &o)
 {
 	const int lane = threadIdx.x & 31;
@@ -467,7 +482,7 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 #pragma unroll
 	for (int j = 0; j < CPT; ++j) {
 		const int tp = ext[j] ? h0[j] + 1 : 0, qp = ext[j] ? d0 + j + h0[j] + 1 : 0;
-		px[j] = seq4(T, tp) ^ seq4(Q, qp);
+		px[j] = sv.probe(tp, qp);
 	}
 	stsv<CPT>(sb + q1.z, o.E1); stsv<CPT>(sb + q1.w, o.F1); stsv<CPT>(sb + q2.z, o.E2); stsv<CPT>(sb + q2.w, o.F2);
 	bool more = false;
@@ -475,7 +490,7 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 #pragma unroll
 	for (int j = 0; j < CPT; ++j) {
 		const int kmax = kmin[j] + kspan[j];
-		const int adv = __clz(__brev(px[j])) >> 3; /* index of the first differing byte; 4 when all four match */
+		const int adv = sv.advance(px[j]); /* positions up to the first difference; the whole word when all match */
 		const int k = min(h0[j] + adv, kmax);
 		unres[j] = ext[j] && px[j] == 0 && k < kmax;
 		more |= unres[j];
@@ -484,7 +499,7 @@ __device__ __forceinline__ int tile_cells(uint32_t sb, const int4 &qh, const int
 	if (more) { /* rare: a run longer than the first probe */
 #pragma unroll
 		for (int j = 0; j < CPT; ++j)
-			if (unres[j]) o.H[j] = tile_extend_more(T, Q, o.H[j], d0 + j, kmin[j] + kspan[j]);
+			if (unres[j]) o.H[j] = tile_extend_more(sv, o.H[j], d0 + j, kmin[j] + kspan[j]);
 	}
 	if (EDGE && useful && dfin >= d0 && dfin < d0 + CPT) { /* end of both sequences, :405-409 */
 #pragma unroll
@@ -515,7 +530,7 @@ __device__ __forceinline__ void step_arrive(uint64_t *bar)
 template<int MODE>
 __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, const int4 &q1, const int4 &q2, int d0,
                                                    const int (&kmin)[4], const int (&kspan)[4],
-                                                   const uint32_t *__restrict__ T, const uint32_t *__restrict__ Q,
+                                                   const SeqView &sv,
                                                    bool no_left, bool no_right, uint64_t *stepbar, bool wait, uint32_t parity, CellOut<4> &o)
 {
 	const int lane = threadIdx.x & 31;
@@ -552,7 +567,7 @@ __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, 
 		o.E1[j] = E1, o.E2[j] = E2, o.F1[j] = F1, o.F2[j] = F2, h0[j] = H; \
 		ext[j] = (unsigned)(H - kmin[j]) <= (unsigned)kspan[j]; \
 		const int tp = ext[j] ? H + 1 : 0, qp = ext[j] ? d0 + j + H + 1 : 0; \
-		px[j] = seq4(T, tp) ^ seq4(Q, qp); \
+		px[j] = sv.probe(tp, qp); \
 	} while (0)
 	TILE_CELL(1);
 	TILE_CELL(2);
@@ -579,7 +594,7 @@ __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, 
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		const int kmax = kmin[j] + kspan[j];
-		const int adv = __clz(__brev(px[j])) >> 3;
+		const int adv = sv.advance(px[j]);
 		const int k = min(h0[j] + adv, kmax);
 		unres[j] = ext[j] && px[j] == 0 && k < kmax;
 		more |= unres[j];
@@ -588,7 +603,7 @@ __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, 
 	if (more) {
 #pragma unroll
 		for (int j = 0; j < 4; ++j)
-			if (unres[j]) o.H[j] = tile_extend_more(T, Q, o.H[j], d0 + j, kmin[j] + kspan[j]);
+			if (unres[j]) o.H[j] = tile_extend_more(sv, o.H[j], d0 + j, kmin[j] + kspan[j]);
 	}
 	stsv<4>(sb + qh.w, o.H);
 	o.tb = tbw;
@@ -669,7 +684,10 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
 		}
 		if (tid < 3) sc[tid] = 0;
-		const uint32_t *T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), *Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off);
+		SeqView sv;
+		if (P.packed && P.packed[pi]) /* two-bit codes, 16 per word, at a quarter of the raw offsets */
+			sv.T = P.seqp + (pd.t_off >> 4), sv.Q = P.seqp + (pd.q_off >> 4), sv.s_idx = 4, sv.s_amt = 1, sv.s_adv = 1;
+		else sv.T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), sv.Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off), sv.s_idx = 2, sv.s_amt = 3, sv.s_adv = 3;
 		const int c = CPT * tid, d0 = idx0 + c - doff;
 		const bool useful = c >= HL && c < HL + ulen;
 		const bool special = left_edge || right_edge || (dfin >= idx0 - doff && dfin < idx0 - doff + W); /* flags matter */
@@ -710,7 +728,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				for (int t = 1; t <= Tb; ++t) {
 					hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
 					const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-					tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, T, Q, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
+					tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, sv, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
 					if (t > 1) ++step_phase;
 					if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
 					if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
@@ -725,7 +743,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 			for (int t = 1; t <= Tb; ++t) {
 				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
 				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-				tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, o);
+				tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
 				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
 				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
 				__syncthreads();
@@ -738,9 +756,9 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
 				const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
 				if (edge) {
-					const int myfl = tile_cells<MODE, true, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, o);
+					const int myfl = tile_cells<MODE, true, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
 					if (myfl) atomicOr(&sc[t % 3], myfl);
-				} else tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, T, Q, no_left, no_right, useful, o);
+				} else tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
 				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
 				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
 				if (tid == 0) {
@@ -1024,6 +1042,64 @@ __global__ void wfa_tile_ckpt_seg_kernel(const TParams P, int j)
 		t.i = i, t.k = k, t.row = row, t.last = last;
 		if (ks < 0) t.fwd_status = TS_IDLE; /* every checkpoint found: the earlier segments need no recompute */
 		*tsp = t;
+	}
+}
+
+
+/* Two-bit packing of the pairs whose two sequences use at most 4 distinct byte values together (DNA): a presence bitmap of the
+ * pair, codes = rank of the byte among the values present (so equal codes <=> equal bytes), 16 codes per 32-bit word,
+ * position p in bits 2(p%16).  One CTA of 256 threads per pair.  Bytes past the end of a sequence become arbitrary codes; the
+ * match run is clamped to the matrix anyway. */
+__global__ void __launch_bounds__(256) wfa_pack2_kernel(const uint8_t *__restrict__ seq, const PairDesc *__restrict__ pairs, uint32_t *__restrict__ seqp, int *__restrict__ packed)
+{
+	__shared__ unsigned int bm[8];
+	__shared__ unsigned char lut[256];
+	__shared__ int ok;
+	const int pi = blockIdx.x, tid = threadIdx.x;
+	const PairDesc pd = pairs[pi];
+	if (tid < 8) bm[tid] = 0;
+	__syncthreads();
+	unsigned int loc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	for (int which = 0; which < 2; ++which) {
+		const uint8_t *p = seq + (which ? pd.q_off : pd.t_off);
+		const int len = which ? pd.ql : pd.tl;
+		for (long long i = (long long)tid * 16; i < len; i += 256 * 16) {
+			const uint4 v = *reinterpret_cast<const uint4*>(p + i);
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+			for (int b = 0; b < 16; ++b)
+				if (i + b < len) { const unsigned int c = w[b >> 2] >> (8 * (b & 3)) & 0xffu; loc[c >> 5] |= 1u << (c & 31); }
+		}
+	}
+#pragma unroll
+	for (int w = 0; w < 8; ++w) if (loc[w]) atomicOr(&bm[w], loc[w]);
+	__syncthreads();
+	if (tid == 0) {
+		int cnt = 0;
+		for (int w = 0; w < 8; ++w) cnt += __popc(bm[w]);
+		ok = cnt <= 4;
+		packed[pi] = ok;
+	}
+	{
+		int r = __popc(bm[tid >> 5] & ((1u << (tid & 31)) - 1u));
+		for (int w = 0; w < (tid >> 5); ++w) r += __popc(bm[w]);
+		lut[tid] = (unsigned char)(r & 3);
+	}
+	__syncthreads();
+	if (!ok) return;
+	for (int which = 0; which < 2; ++which) {
+		const long long off = which ? pd.q_off : pd.t_off;
+		const uint8_t *p = seq + off;
+		const int n_words = ((which ? pd.ql : pd.tl) + 15) / 16 + 3; /* the probe reads one word ahead, the long-run loop four */
+		uint32_t *out = seqp + (off >> 4);
+		for (int wi = tid; wi < n_words; wi += 256) {
+			const uint4 v = *reinterpret_cast<const uint4*>(p + (long long)wi * 16);
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			uint32_t code = 0;
+#pragma unroll
+			for (int b = 0; b < 16; ++b) code |= (uint32_t)lut[w[b >> 2] >> (8 * (b & 3)) & 0xffu] << (2 * b);
+			out[wi] = code;
+		}
 	}
 }
 
