@@ -530,13 +530,17 @@ __device__ __forceinline__ void step_arrive(uint64_t *bar)
 template<int MODE>
 __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, const int4 &q1, const int4 &q2, int d0,
                                                    const int (&kmin)[4], const int (&kspan)[4],
-                                                   const SeqView &sv,
+                                                   const SeqView &sv, bool reuse_e2,
                                                    bool no_left, bool no_right, uint64_t *stepbar, bool wait, uint32_t parity, CellOut<4> &o)
 {
 	const int lane = threadIdx.x & 31;
 	int ho1[4], pe1[4], pf1[4], ho2[4], pe2[4], pf2[4], hx[4];
 	ldsv<4>(sb + qh.y, ho1); ldsv<4>(sb + q1.x, pe1); ldsv<4>(sb + q1.y, pf1); ldsv<4>(sb + qh.z, ho2);
-	ldsv<4>(sb + q2.x, pe2); ldsv<4>(sb + q2.y, pf2); ldsv<4>(sb + qh.x, hx);
+	if (reuse_e2) { /* e2 == 1: E2 / F2 of the previous score are this thread's own cells of the previous step, still in registers */
+#pragma unroll
+		for (int j = 0; j < 4; ++j) pe2[j] = o.E2[j], pf2[j] = o.F2[j];
+	} else { ldsv<4>(sb + q2.x, pe2); ldsv<4>(sb + q2.y, pf2); }
+	ldsv<4>(sb + qh.x, hx);
 	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
@@ -588,7 +592,8 @@ __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, 
 	TILE_CELL(0);
 	TILE_CELL(3);
 #undef TILE_CELL
-	stsv<4>(sb + q1.z, o.E1); stsv<4>(sb + q1.w, o.F1); stsv<4>(sb + q2.z, o.E2); stsv<4>(sb + q2.w, o.F2);
+	stsv<4>(sb + q1.z, o.E1); stsv<4>(sb + q1.w, o.F1);
+	stsv<4>(sb + q2.z, o.E2); stsv<4>(sb + q2.w, o.F2);
 	bool more = false;
 	bool unres[4];
 #pragma unroll
@@ -728,7 +733,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				for (int t = 1; t <= Tb; ++t) {
 					hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
 					const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-					tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, sv, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
+					tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, sv, t > 1 && P.pen.e2 == 1, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
 					if (t > 1) ++step_phase;
 					if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
 					if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
