@@ -902,7 +902,7 @@ struct mwf_b200_batch {
 	int n_geom, tR, wave_pairs, s_limit;
 	long long max_len, max_sbound, arena_full; /* arena_full: the arena when everything that is free is taken */
 	int *d_nseg;
-	uint32_t *d_seqp; /* two-bit packed sequences */
+	uint32_t *d_seqp; /* two- or four-bit packed sequences */
 	int *d_packed;
 	/* segmented traceback */
 	int seg_P;
@@ -1104,7 +1104,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		ws_dev(&b->d_items, sizeof(int2) * b->items_cap, b->dev);
 		ws_dev(&b->d_tmisc, 128, b->dev);
 		if (env_int("MWF_B200_TILE_PACK", 1)) {
-			ws_dev(&b->d_seqp, b->seq_bytes / 4 + 256, b->dev);
+			ws_dev(&b->d_seqp, b->seq_bytes / 2 + 256, b->dev);
 			ws_dev(&b->d_packed, sizeof(int) * std::max(1, n_pairs), b->dev);
 		}
 		ws_host(&b->h_running, 2 * 64);
@@ -1170,8 +1170,8 @@ extern "C" void mwf_b200_batch_upload(mwf_b200_batch_t *b, const char *const *ts
 	CUDA_OK(cudaMemcpyAsync(b->d_pairs, b->pairs.data(), sizeof(PairDesc) * b->n, cudaMemcpyHostToDevice, b->stream));
 	CUDA_OK(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int) * b->n, cudaMemcpyHostToDevice, b->stream));
 	b->h2d = (int64_t)b->seq_bytes + (int64_t)(sizeof(PairDesc) + sizeof(int)) * b->n;
-	if (b->d_seqp && b->n > 0) { /* two-bit copies for the tile engine's match-run probes */
-		wfa_pack2_kernel<<<b->n, 256, 0, b->stream>>>(b->d_seq, b->d_pairs, b->d_seqp, b->d_packed);
+	if (b->d_seqp && b->n > 0) { /* two- or four-bit copies for the tile engine's match-run probes */
+		wfa_pack_kernel<<<b->n, 256, 0, b->stream>>>(b->d_seq, b->d_pairs, b->d_seqp, b->d_packed);
 		CUDA_OK(cudaGetLastError());
 	}
 }

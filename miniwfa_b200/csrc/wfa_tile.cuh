@@ -62,8 +62,8 @@ struct TParams {
 	const PairDesc *pairs;
 	PairOut *outs;
 	const uint8_t *seq;
-	const uint32_t *seqp;      /* two-bit packed copies (wfa_pack2_kernel), word offset = raw byte offset / 16 */
-	const int *packed;         /* [pair index]: 1 when the pair was packed */
+	const uint32_t *seqp;      /* packed copies (wfa_pack_kernel), word offset = raw byte offset / 8 */
+	const int *packed;         /* [pair index]: bits per code (2 or 4), 0 when the pair stays on raw bytes */
 	uint32_t *cigar;
 	TileCtl *ctl;              /* [n_pairs] */
 	int32_t *state;            /* [n_pairs][2][R][pitch] */
@@ -690,8 +690,11 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 		}
 		if (tid < 3) sc[tid] = 0;
 		SeqView sv;
-		if (P.packed && P.packed[pi]) /* two-bit codes, 16 per word, at a quarter of the raw offsets */
-			sv.T = P.seqp + (pd.t_off >> 4), sv.Q = P.seqp + (pd.q_off >> 4), sv.s_idx = 4, sv.s_amt = 1, sv.s_adv = 1;
+		const int code_bits = P.packed ? P.packed[pi] : 0;
+		if (code_bits == 2) /* two-bit codes, 16 per word */
+			sv.T = P.seqp + (pd.t_off >> 3), sv.Q = P.seqp + (pd.q_off >> 3), sv.s_idx = 4, sv.s_amt = 1, sv.s_adv = 1;
+		else if (code_bits == 4) /* four-bit codes, 8 per word */
+			sv.T = P.seqp + (pd.t_off >> 3), sv.Q = P.seqp + (pd.q_off >> 3), sv.s_idx = 3, sv.s_amt = 2, sv.s_adv = 2;
 		else sv.T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), sv.Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off), sv.s_idx = 2, sv.s_amt = 3, sv.s_adv = 3;
 		const int c = CPT * tid, d0 = idx0 + c - doff;
 		const bool useful = c >= HL && c < HL + ulen;
@@ -1051,15 +1054,15 @@ __global__ void wfa_tile_ckpt_seg_kernel(const TParams P, int j)
 }
 
 
-/* Two-bit packing of the pairs whose two sequences use at most 4 distinct byte values together (DNA): a presence bitmap of the
- * pair, codes = rank of the byte among the values present (so equal codes <=> equal bytes), 16 codes per 32-bit word,
- * position p in bits 2(p%16).  One CTA of 256 threads per pair.  Bytes past the end of a sequence become arbitrary codes; the
- * match run is clamped to the matrix anyway. */
-__global__ void __launch_bounds__(256) wfa_pack2_kernel(const uint8_t *__restrict__ seq, const PairDesc *__restrict__ pairs, uint32_t *__restrict__ seqp, int *__restrict__ packed)
+/* Packing of the pairs whose two sequences together use at most 4 (DNA) or at most 16 (DNA with N, soft-masked, IUPAC) distinct
+ * byte values: a presence bitmap of the pair, codes = rank of the byte among the values present (so equal codes <=> equal bytes),
+ * 2 or 4 bits per code, 16 or 8 codes per 32-bit word, position p in bits c(p % (32/c)).  One CTA of 256 threads per pair.
+ * Bytes past the end of a sequence become arbitrary codes; the match run is clamped to the matrix anyway. */
+__global__ void __launch_bounds__(256) wfa_pack_kernel(const uint8_t *__restrict__ seq, const PairDesc *__restrict__ pairs, uint32_t *__restrict__ seqp, int *__restrict__ packed)
 {
 	__shared__ unsigned int bm[8];
 	__shared__ unsigned char lut[256];
-	__shared__ int ok;
+	__shared__ int sh_bits;
 	const int pi = blockIdx.x, tid = threadIdx.x;
 	const PairDesc pd = pairs[pi];
 	if (tid < 8) bm[tid] = 0;
@@ -1082,31 +1085,40 @@ __global__ void __launch_bounds__(256) wfa_pack2_kernel(const uint8_t *__restric
 	if (tid == 0) {
 		int cnt = 0;
 		for (int w = 0; w < 8; ++w) cnt += __popc(bm[w]);
-		ok = cnt <= 4;
-		packed[pi] = ok;
+		sh_bits = cnt <= 4 ? 2 : cnt <= 16 ? 4 : 0;
+		packed[pi] = sh_bits;
 	}
 	{
 		int r = __popc(bm[tid >> 5] & ((1u << (tid & 31)) - 1u));
 		for (int w = 0; w < (tid >> 5); ++w) r += __popc(bm[w]);
-		lut[tid] = (unsigned char)(r & 3);
+		lut[tid] = (unsigned char)(r & 15);
 	}
 	__syncthreads();
-	if (!ok) return;
+	const int bits = sh_bits;
+	if (bits == 0) return;
+	const int cpw = 32 / bits; /* codes per word */
 	for (int which = 0; which < 2; ++which) {
 		const long long off = which ? pd.q_off : pd.t_off;
 		const uint8_t *p = seq + off;
-		const int n_words = ((which ? pd.ql : pd.tl) + 15) / 16 + 3; /* the probe reads one word ahead, the long-run loop four */
-		uint32_t *out = seqp + (off >> 4);
+		const int n_words = ((which ? pd.ql : pd.tl) + cpw - 1) / cpw + 5; /* the probe reads one word ahead, the long-run loop four */
+		uint32_t *out = seqp + (off >> 3);
 		for (int wi = tid; wi < n_words; wi += 256) {
-			const uint4 v = *reinterpret_cast<const uint4*>(p + (long long)wi * 16);
-			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			const uint8_t *src = p + (long long)wi * cpw;
 			uint32_t code = 0;
+			if (bits == 2) {
+				const uint4 v = *reinterpret_cast<const uint4*>(src);
+				const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-			for (int b = 0; b < 16; ++b) code |= (uint32_t)lut[w[b >> 2] >> (8 * (b & 3)) & 0xffu] << (2 * b);
+				for (int b = 0; b < 16; ++b) code |= (uint32_t)(lut[w[b >> 2] >> (8 * (b & 3)) & 0xffu] & 3) << (2 * b);
+			} else {
+				const uint2 v = *reinterpret_cast<const uint2*>(src);
+				const uint32_t w[2] = { v.x, v.y };
+#pragma unroll
+				for (int b = 0; b < 8; ++b) code |= (uint32_t)lut[w[b >> 2] >> (8 * (b & 3)) & 0xffu] << (4 * b);
+			}
 			out[wi] = code;
 		}
 	}
 }
-
 
 #endif
