@@ -332,3 +332,28 @@ def test_segmented_traceback(monkeypatch):
     monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", "0")
     for (t, q), w in zip(pairs[3:9], want[0][3:9]):
         assert mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR), t, q) == w
+
+
+def test_reference_cli_linked_against_this_library(tmp_path):
+    """the reference's own, unmodified main.c, compiled against include/miniwfa.h and linked with
+    libminiwfa_b200.so in place of miniwfa.o kalloc.o mwf-dbg.o (oracle/_ref/test-mwf-dropin, built where /root/reference
+    exists), prints the reference's lines."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "test-mwf-dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/test-mwf-dropin was not built (needs /root/reference at build time)")
+    t3 = ("CAGGGGCAGACTGACACTTCACACGGCCGGGTACTCTAACAGACCTGCAGCTGAGGGTCCT",
+          "TAGGGGCAGACTGACACCTCACACGGCCGGGTACTCCTCTGAGACAAAACTTCCAGAGGAACGATCAGACAGCAGCATTCGCGGTTCATGAAAATCCGCTGTTCTG"
+          "CAGCCACCGCTGCTGGTACCCAGGCAAACAGGGTCTAGAGTGGACCTTTAGCAAACTCCAACAGACCTGCAGCTGAGGGTCCT")
+    f1, f2 = tmp_path / "t3-0.fa", tmp_path / "t3-1.fa"
+    f1.write_text(">t3-0\n%s\n" % t3[0])
+    f2.write_text(">t3-1\n%s\n" % t3[1])
+    head = "t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t"
+    want = {"": "155", "-c": "155\t1X16=1X14=128I4=1X24=", "-cp5": "155\t1X16=1X14=128I4=1X24=", "-cK": "155\t1X16=1X14=128I4=1X24=",
+            "-ct": "155\t1X16=1X14=128I4=1X24=", "-cu": "155\t1X16=1X18=128I1X24=", "-ca": "272\t1X16=1X18=118I1=10I24=",
+            "-ce": "128\t21I2=6I2=9I1=1I1=10I1=2I1=1I1=1I2=2I1=9I1=1I1=9I1=6I1=4I1=3I1=1I1=5I2=6I1=4I1=2I1=1I3=3I1=3I1=4I1=1I2=2I1=1I1=2I1=6I2=2I24="}
+    for flags, tail in want.items():
+        out = subprocess.run([exe] + ([flags] if flags else []) + [str(f1), str(f2)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        assert out.stdout.strip() == head + tail, (flags, out.stdout)
