@@ -118,3 +118,21 @@ def test_no_cpu_fallback_symbols(product_lib):
     """The product library must not embed the oracle."""
     out = os.popen("nm -D %s" % api.LIB_PATH).read()
     assert "orc_" not in out
+
+
+def test_reference_cli_links_against_the_library(product_lib):
+    """Where /root/reference exists: its unmodified main.c compiles against include/miniwfa.h and links with the product library
+    in place of miniwfa.o kalloc.o mwf-dbg.o (the drop-in of INTEGRATION.md 1); every API symbol it needs resolves to us."""
+    import shutil
+    import subprocess
+    import pytest
+    if not os.path.exists("/root/reference/main.c"):
+        pytest.skip("/root/reference is not present on this machine")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.STDOUT)
+    exe = os.path.join(ROOT, "oracle", "_ref", "test-mwf-dropin")
+    assert os.path.exists(exe)
+    und = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True, check=True).stdout
+    assert {"mwf_opt_init", "mwf_wfa_exact", "mwf_wfa_chain", "mwf_wfa_auto", "mwf_assert_cigar"} <= {ln.split()[-1] for ln in und.splitlines() if ln.split()}
+    if shutil.which("ldd"):
+        out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+        assert "libminiwfa_b200.so" in out and "not found" not in out.split("libminiwfa_b200.so")[1].split("\n")[0]
