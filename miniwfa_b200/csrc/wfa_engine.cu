@@ -1094,6 +1094,11 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		free_b += ws_cached_bytes(b->dev); /* cached workspaces are reused or given back on demand */
 		const double frac = b->is_tb ? 0.35 : 0.85;
 		b->wave_pairs = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, n_pairs), (size_t)(free_b * frac) / per_pair));
+		if (b->is_tb && n_pairs > 1) { /* ... and few enough that their expected traceback bytes (s ~ 0.3 n) fit the arena in one go */
+			const double len = 0.5 * (double)max_len, expect = 0.09 * len * len + 4096.0 * len;
+			const double room = (double)free_b * 0.5;
+			b->wave_pairs = (int)std::max(1.0, std::min((double)b->wave_pairs, room / expect));
+		}
 		if (env_int("MWF_B200_TILE_WAVE", 0) > 0) b->wave_pairs = std::min(b->wave_pairs, env_int("MWF_B200_TILE_WAVE", 0)); /* tests */
 		const int wp = b->wave_pairs;
 		if (ws_dev(&b->d_state, (size_t)wp * 2 * b->tR * b->pitch * 4, b->dev)) /* fresh memory: a large negative int32 everywhere */
