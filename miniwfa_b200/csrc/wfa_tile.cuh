@@ -23,7 +23,11 @@
  * per-diagonal "alive" words the tiles accumulate over the last nring scores, and cuts the next block.
  *
  * Kernels: wfa_tile_init_kernel (score 0), wfa_plan_kernel (one CTA per pair, between blocks),
- * wfa_tile_kernel<MODE> (persistent CTAs pulling (pair, tile) items), wfa_tile_traceback_kernel.
+ * wfa_tile_kernel<MODE, CPT> (persistent CTAs pulling (pair, tile) items; CPT = cells per thread: 4 when a launch has enough
+ * tiles to fill the GPU -- with a split-phase step barrier in interior tiles -- and 1 on the same 512-wide tile otherwise),
+ * wfa_pack_kernel (two- / four-bit copies of the sequences for the match-run probes), wfa_tile_traceback_kernel;
+ * low-memory mode: wfa_tile_checkpoint_kernel; traceback beyond s^2 bytes of HBM: snapshots taken by the tiles, then
+ * wfa_tile_segstart_kernel, wfa_tile_trace_seg_kernel / wfa_tile_ckpt_seg_kernel per segment.
  */
 #ifndef WFA_TILE_CUH
 #define WFA_TILE_CUH
@@ -100,15 +104,8 @@ struct TParams {
 /* index of diagonal 0 in a state row: independent of the tile geometry, so that the geometry may change between launches */
 __device__ __forceinline__ int tile_doff(const TParams &P, int tl) { return tl + P.pen.nring + TILE_TMAX + 8; }
 
-/* row index inside a state buffer / the shared-memory tile */
-struct RowMap {
-	int nring, d1, d2, bE1, bF1, bE2, bF2;
-	__device__ __forceinline__ RowMap(const Pen &p)
-	{
-		nring = p.nring, d1 = p.e1 + 1, d2 = p.e2 + 1;
-		bE1 = nring, bF1 = bE1 + d1, bE2 = bF1 + d1, bF2 = bE2 + d2;
-	}
-};
+/* Row index inside a state buffer / the shared-memory tile: H of score s in row s % nring; then E1, F1 (depth e1+1 each) and
+ * E2, F2 (depth e2+1 each).  The byte offsets a score needs are tabulated on the host (tabH / tabE1 / tabE2 in TParams). */
 
 /* ------------------------------------------------------------------------------------------ */
 /* bulk-copy (TMA, non-tensor form) + mbarrier helpers                                          */
@@ -642,7 +639,7 @@ template<int CPT> __device__ __forceinline__ void store_tb(uint8_t *p, uint32_t 
 /* threads per CTA and CTAs per SM the kernel is compiled for: 4 cells per thread keeps the instruction count per cell lowest
  * (batches); 2 and 1 cells per thread put 2x / 4x the threads on a tile, which shortens the dependent chain of one score
  * step when there are too few tiles to fill the GPU (single large pairs) */
-#define TILE_MAX_THREADS(CPT) ((CPT) == 4 ? 512 : 512)
+#define TILE_MAX_THREADS(CPT) 512
 #define TILE_MIN_CTAS(CPT) ((CPT) == 4 ? 1 : 2)
 
 /* shared memory: rows[R][W] int32 | ctl ints [16] (flags, item, mbarrier) */
