@@ -334,9 +334,13 @@ def main():
                 "launches_per_pass": per_pass,
                 "kernel_ms": kernel_ms[0], "kernel_ms_max_over_ranks": k_ms,
                 "note": "one pass over the batch = launches_per_pass launches (score-0 init, then one plan + one tile kernel per block "
-                        "of 64 scores); kernel_ms is the CUDA-event time over all of them on the launching stream, so achieved = "
-                        "cells_per_pass x 64 B / kernel_ms understates the tile kernel alone; the tile engine keeps the ring in shared "
-                        "memory, so its DRAM traffic (`traffic`, per pass, from ncu) is far below the algorithmic bytes"}
+                        "of 32 scores); kernel_ms is the CUDA-event time over all of them on the launching stream, so achieved = "
+                        "cells_per_pass x 64 B / kernel_ms understates the tile kernel alone. frac > 1 is expected here and is not a "
+                        "skipped-work artefact: the 64 B/cell are what the reference's formulation streams per cell (SURVEY 8d), while "
+                        "the tile engine keeps the 27 live ring rows in shared memory for 32 scores, so its measured DRAM traffic "
+                        "(`traffic`, bytes per pass, ncu launch list in profiles/) is ~6 B/cell; every cell is computed (r.n_iter and "
+                        "r.s equal the CPU reference's). What limits the kernel now is instruction issue (68 % of peak, 80 "
+                        "instructions per cell) and the L1 data pipe (68 %): profiles/r1_tile_kernel.md"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
