@@ -84,6 +84,20 @@ void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pairs,
                          const int32_t *tl, const char *const *ts,
                          const int32_t *ql, const char *const *qs, mwf_rst_t *r);
 
+/* The k-mer front end of mwf_wfa_chain on the device (kmer_front.cuh); sequences are host buffers, as everywhere in this API.
+ *
+ * mwf_b200_kmer_hits replaces mg_fc_kmer x 2 + radix_sort_mwf64 + the match loop + radix_sort_mwf64 + the word swap of
+ * mg_chain (miniwfa.c:737-770): every (target position, query position) pair of a shared k-mer that has at most max_occ
+ * copies in either sequence, as query << 32 | target (positions of the k-mer's last base), in ascending (target, query)
+ * order -- the array mg_lis_64 runs on.  Returns their number; *hits is pinned host memory owned by the library
+ * (NULL when there are none), to be released with mwf_b200_kmer_free. */
+int64_t mwf_b200_kmer_hits(int32_t tl, const char *ts, int32_t ql, const char *qs, int32_t k, int32_t max_occ, uint64_t **hits);
+void    mwf_b200_kmer_free(uint64_t *hits);
+/* The counting part of mwf_ksim (miniwfa.c:786-812): k-mers in s1, k-mers in s2, sum over distinct k-mers of
+ * min(copies in s1, copies in s2).  The caller does the two divisions. */
+void    mwf_b200_kmer_shared(int32_t l1, const char *s1, int32_t l2, const char *s2, int32_t k, int64_t *n1, int64_t *n2, int64_t *shared);
+int64_t mwf_b200_kmer_launches(void); /* kernels launched by the two calls above since the library was loaded */
+
 #ifdef __cplusplus
 }
 #endif

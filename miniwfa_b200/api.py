@@ -64,6 +64,16 @@ def lib():
         L.mwf_b200_batch_kernel_used.restype = ctypes.c_int
         L.mwf_b200_release_cache.argtypes = []
         L.mwf_b200_release_cache.restype = None
+        L.mwf_b200_kmer_hits.argtypes = [i32, ctypes.c_char_p, i32, ctypes.c_char_p, i32, i32,
+                                         ctypes.POINTER(ctypes.POINTER(ctypes.c_uint64))]
+        L.mwf_b200_kmer_hits.restype = i64
+        L.mwf_b200_kmer_free.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+        L.mwf_b200_kmer_free.restype = None
+        L.mwf_b200_kmer_shared.argtypes = [i32, ctypes.c_char_p, i32, ctypes.c_char_p, i32,
+                                           ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        L.mwf_b200_kmer_shared.restype = None
+        L.mwf_b200_kmer_launches.argtypes = []
+        L.mwf_b200_kmer_launches.restype = i64
         L.kfree.argtypes = [vp, vp]
         L.km_init.restype = vp
         L.km_destroy.argtypes = [vp]
@@ -113,6 +123,28 @@ def wfa_auto(opt, ts, qs, km=None):
     r = MwfRst()
     lib().mwf_wfa_auto(km, ctypes.byref(opt), len(ts), ts, len(qs), qs, ctypes.byref(r))
     return _take(r, km)
+
+
+def wfa_chain(opt, ts, qs, km=None):
+    r = MwfRst()
+    lib().mwf_wfa_chain(km, ctypes.byref(opt), len(ts), ts, len(qs), qs, ctypes.byref(r))
+    return _take(r, km)
+
+
+def kmer_hits(ts, qs, k, max_occ):
+    """mwf_b200_kmer_hits -> list of query << 32 | target words in ascending (target, query) order."""
+    p = ctypes.POINTER(ctypes.c_uint64)()
+    n = lib().mwf_b200_kmer_hits(len(ts), ts, len(qs), qs, k, max_occ, ctypes.byref(p))
+    out = [p[i] for i in range(n)]
+    lib().mwf_b200_kmer_free(p)
+    return out
+
+
+def kmer_shared(s1, s2, k):
+    """mwf_b200_kmer_shared -> (k-mers in s1, k-mers in s2, sum of min(copies) over distinct k-mers)."""
+    a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    lib().mwf_b200_kmer_shared(len(s1), s1, len(s2), s2, k, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return a.value, b.value, c.value
 
 
 def _arrays(pairs):

@@ -17,9 +17,18 @@
 #include <stdlib.h>
 #include <string.h>
 #include <assert.h>
+#include <stdio.h>
+#include <time.h>
 #include "miniwfa.h"
 #include "mwf_b200.h"
 #include "kalloc.h"
+
+static double now_ms(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return 1e3 * (double)t.tv_sec + 1e-6 * (double)t.tv_nsec;
+}
 
 /* ---- CIGAR assembly (reference :46-62, :816-827) ---- */
 
@@ -103,37 +112,78 @@ static void sort64(void *km, uint64_t *a, size_t n)
 	kfree(km, tmp);
 }
 
-/* longest strictly increasing subsequence of v[0..n); writes the chosen indices to pick[], returns their number (:678-697) */
+/* longest strictly increasing subsequence of v[0..n); writes the chosen indices to pick[], returns their number (:678-697).
+ * tailv[l] / tail[l] = value / index of the smallest last element of an increasing chain of length l (tailv is strictly
+ * increasing in l).  An element x goes behind the longest chain whose last value is below it, lo = max { l : tailv[l] < x }.
+ * On similar sequences that chain is nearly always among the longest few, so the search first gallops down from the top; a
+ * stray match (~10 % of the matches of a 3 %-divergent pair) lands anywhere in an array of tens of MB, and bisecting that costs
+ * a dozen cache misses -- those go through samp[b] = tailv[64 b], which stays in cache, and then one 64-entry block.
+ * Same lo as plain bisection, so the same chain as the reference's mg_lis_64. */
+#define LIS_BLK 64
+
 static int32_t longest_increasing(void *km, int32_t n, const uint64_t *v, int32_t *pick)
 {
 	int32_t *tail, *prev, i, len = 0, at;
+	uint64_t *tailv, *samp;
 	if (n <= 0) return 0;
-	tail = (int32_t*)kmalloc(km, sizeof(int32_t) * ((size_t)n + 1)); /* tail[l] = index ending the best chain of length l */
+	tail = (int32_t*)kmalloc(km, sizeof(int32_t) * ((size_t)n + 1));
+	tailv = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)n + 1));
+	samp = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)n / LIS_BLK + 2));
 	prev = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)n);
 	for (i = 0; i < n; ++i) {
-		int32_t lo = 0, hi = len; /* number of tails strictly below v[i] */
-		while (lo < hi) {
-			const int32_t mid = (lo + hi + 1) >> 1;
-			if (v[tail[mid]] < v[i]) lo = mid; else hi = mid - 1;
+		const uint64_t x = v[i];
+		int32_t lo = len;
+		if (len > 0 && tailv[len] >= x) {
+			int32_t hi = len, step = 1; /* invariant: tailv[hi] >= x */
+			lo = hi - 1;
+			while (lo > 0 && tailv[lo] >= x && step < LIS_BLK) hi = lo, step <<= 1, lo = hi - step;
+			if (lo > 0 && tailv[lo] >= x) { /* far below the top */
+				int32_t bl = 0, bh = lo / LIS_BLK + 1; /* samp[bl] < x (or bl == 0), samp[bh] >= x (or bh past the last block) */
+				hi = lo;
+				while (bh - bl > 1) {
+					const int32_t bm = bl + ((bh - bl) >> 1);
+					if (samp[bm] < x) bl = bm; else bh = bm;
+				}
+				lo = bl * LIS_BLK;
+				if (lo + LIS_BLK < hi) hi = lo + LIS_BLK; /* = LIS_BLK * bh, and samp[bh] >= x */
+			}
+			if (lo < 0) lo = 0;
+			while (hi - lo > 1) {
+				const int32_t mid = lo + ((hi - lo) >> 1);
+				if (tailv[mid] < x) lo = mid; else hi = mid;
+			}
 		}
 		prev[i] = lo > 0 ? tail[lo] : -1;
-		tail[lo + 1] = i;
+		tail[lo + 1] = i, tailv[lo + 1] = x;
+		if ((lo + 1) % LIS_BLK == 0) samp[(lo + 1) / LIS_BLK] = x;
 		if (lo + 1 > len) len = lo + 1;
 	}
 	for (i = len - 1, at = tail[len]; i >= 0; --i) pick[i] = at, at = prev[at];
 	kfree(km, prev);
+	kfree(km, samp);
+	kfree(km, tailv);
 	kfree(km, tail);
 	return len;
 }
 
-/* anchors (target position << 32 | query position, last base of the k-mer) of the best co-linear chain (:732-784) */
-static uint64_t *chain_anchors(void *km, int32_t tl, const char *ts, int32_t ql, const char *qs, int k, int max_occ, int32_t *n_out)
+/* Where the k-mer lists are built, sorted and matched: on the device (kmer_front.cuh) from FRONT_MIN_BASES bases up, on the
+ * host below that (a few launches and two synchronisations cost more than sorting a few thousand keys here).
+ * MWF_B200_CHAIN_FRONT=gpu|host forces one of the two (tests). */
+#define FRONT_MIN_BASES 4096
+
+static int front_on_device(int64_t bases)
 {
-	uint64_t *km_list, *hit = 0, *anchors;
-	int32_t n_km, n_hit = 0, cap_hit = 0, i, g0, *pick, n_pick;
-	*n_out = 0;
-	if (tl < k || ql < k) return 0;
-	assert(k >= 2 && k <= 15);
+	const char *v = getenv("MWF_B200_CHAIN_FRONT");
+	if (v && !strcmp(v, "gpu")) return 1;
+	if (v && !strcmp(v, "host")) return 0;
+	return bases >= FRONT_MIN_BASES;
+}
+
+/* k-mer matches as (query position << 32 | target position), in ascending (target, query) order (:737-770), on the host */
+static uint64_t *host_hits(void *km, int32_t tl, const char *ts, int32_t ql, const char *qs, int k, int max_occ, int32_t *n_out)
+{
+	uint64_t *km_list, *hit = 0;
+	int32_t n_km, n_hit = 0, cap_hit = 0, i, g0;
 	km_list = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)tl + ql));
 	n_km = list_kmers(tl, ts, 0, k, km_list);
 	n_km += list_kmers(ql, qs, 1, k, km_list + n_km);
@@ -156,13 +206,36 @@ static uint64_t *chain_anchors(void *km, int32_t tl, const char *ts, int32_t ql,
 	kfree(km, km_list);
 	sort64(km, hit, (size_t)n_hit); /* by target position, then query position */
 	for (i = 0; i < n_hit; ++i) hit[i] = hit[i] >> 32 | hit[i] << 32; /* compare on (query, target) */
+	*n_out = n_hit;
+	return hit;
+}
+
+/* anchors (target position << 32 | query position, last base of the k-mer) of the best co-linear chain (:732-784) */
+static uint64_t *chain_anchors(void *km, int32_t tl, const char *ts, int32_t ql, const char *qs, int k, int max_occ, int32_t *n_out)
+{
+	const int on_device = front_on_device((int64_t)tl + ql), timing = getenv("MWF_B200_CHAIN_TIMING") != 0;
+	const double t0 = timing ? now_ms() : 0;
+	double t1 = 0;
+	uint64_t *hit = 0, *anchors;
+	int32_t n_hit = 0, i, *pick, n_pick;
+	*n_out = 0;
+	if (tl < k || ql < k) return 0;
+	assert(k >= 2 && k <= 15);
+	if (on_device) {
+		const int64_t n = mwf_b200_kmer_hits(tl, ts, ql, qs, k, max_occ, &hit);
+		assert(n <= INT32_MAX); /* the reference counts matches in an int32_t (:734) */
+		n_hit = (int32_t)n;
+	} else hit = host_hits(km, tl, ts, ql, qs, k, max_occ, &n_hit);
+	if (timing) t1 = now_ms();
 	pick = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)(n_hit > 0 ? n_hit : 1));
 	n_pick = longest_increasing(km, n_hit, hit, pick);
 	anchors = (uint64_t*)kmalloc(km, sizeof(uint64_t) * (size_t)(n_pick > 0 ? n_pick : 1));
 	for (i = 0; i < n_pick; ++i) anchors[i] = hit[pick[i]] >> 32 | hit[pick[i]] << 32;
 	kfree(km, pick);
-	kfree(km, hit);
+	if (on_device) mwf_b200_kmer_free(hit);
+	else kfree(km, hit);
 	*n_out = n_pick;
+	if (timing) fprintf(stderr, "[mwf_chain] %d k-mer matches in %.2f ms (%s), longest increasing chain %.2f ms\n", n_hit, t1 - t0, on_device ? "device" : "host", now_ms() - t1);
 	return anchors;
 }
 
@@ -191,6 +264,14 @@ static double kmer_similarity(void *km, int32_t l1, const char *s1, int32_t l2, 
 	int32_t n, i, g0, n1 = 0, n2 = 0, t1 = 0, t2 = 0;
 	double p1, p2;
 	if (l1 < k || l2 < k) return 0;
+	if (front_on_device((int64_t)l1 + l2)) {
+		int64_t c1, c2, shared;
+		const double t0 = getenv("MWF_B200_CHAIN_TIMING") ? now_ms() : 0;
+		mwf_b200_kmer_shared(l1, s1, l2, s2, k, &c1, &c2, &shared);
+		if (t0 > 0) fprintf(stderr, "[mwf_chain] shared k-mers of a %d x %d gap in %.2f ms (device)\n", l1, l2, now_ms() - t0);
+		p1 = (double)shared / (double)c1, p2 = (double)shared / (double)c2;
+		return p1 > p2 ? p1 : p2;
+	}
 	a = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)l1 + l2));
 	n = list_kmers(l1, s1, 0, k, a);
 	n += list_kmers(l2, s2, 1, k, a + n);
@@ -223,39 +304,57 @@ void mwf_wfa_chain(void *km, const mwf_opt_t *opt, int32_t tl, const char *ts, i
 {
 	void *km_tmp = !(opt->flag & MWF_F_NO_KALLOC) ? km_init2(km, 0) : 0; /* scratch arena, as the reference's km_wfa (:857) */
 	const int want_cigar = !!(opt->flag & MWF_F_CIGAR);
+	const int timing = getenv("MWF_B200_CHAIN_TIMING") != 0; /* phase times to stderr */
+	const double t0 = timing ? now_ms() : 0;
+	double t1 = 0, t2 = 0, t3 = 0;
 	int32_t n_a, i, x0 = 0, y0 = 0, n_job = 0, score = 0;
 	uint64_t *a = chain_anchors(km_tmp, tl, ts, ql, qs, opt->kmer, opt->max_occ, &n_a);
-	seg_t *seg;
+	seg_t *seg = 0;
+	int32_t n_seg = 0, cap_seg = 0;
 	cigbuf_t c = { 0, 0, 0 };
 
+	if (timing) t1 = now_ms();
+
 	n_a = drop_short_runs(n_a, a, tl, ql, opt->kmer, opt->min_len);
-	seg = (seg_t*)kmalloc(km_tmp, sizeof(seg_t) * ((size_t)n_a + 1));
 	for (i = 0; i <= n_a; ++i) { /* classify what lies between consecutive anchors (:861-889) */
-		seg_t *g = &seg[i];
 		const int32_t x1 = i == n_a ? tl : (int32_t)(a[i] >> 32) + 1, y1 = i == n_a ? ql : (int32_t)(uint32_t)a[i] + 1;
-		g->x0 = x0, g->y0 = y0, g->x1 = x1, g->y1 = y1, g->job = -1;
-		if (i < n_a && x1 - x0 == y1 - y0 && x1 - x0 <= opt->kmer) g->kind = SEG_MATCH; /* inside overlapping k-mer matches */
+		int32_t kind, job = -1;
+		if (i < n_a && x1 - x0 == y1 - y0 && x1 - x0 <= opt->kmer) kind = SEG_MATCH; /* inside overlapping k-mer matches */
 		else if (x0 < x1 && y0 < y1) {
 			if (x1 - x0 >= 10000 && y1 - y0 >= 10000 && kmer_similarity(km, x1 - x0, ts + x0, y1 - y0, qs + y0, opt->kmer) < 0.02)
-				g->kind = SEG_TWO_GAPS; /* two long unrelated stretches: a deletion and an insertion (:869-874) */
-			else g->kind = SEG_EXACT, g->job = n_job++;
-		} else if (x0 < x1) g->kind = SEG_DEL;
-		else if (y0 < y1) g->kind = SEG_INS;
-		else g->kind = SEG_NONE;
+				kind = SEG_TWO_GAPS; /* two long unrelated stretches: a deletion and an insertion (:869-874) */
+			else kind = SEG_EXACT, job = n_job++;
+		} else if (x0 < x1) kind = SEG_DEL;
+		else if (y0 < y1) kind = SEG_INS;
+		else kind = SEG_NONE;
+		/* most anchors are the next base of the same match (millions on a Mb-scale pair): runs of SEG_MATCH become one
+		 * segment -- their CIGAR operations would be merged by cig_add anyway -- and empty segments are not stored */
+		if (kind == SEG_MATCH && n_seg > 0 && seg[n_seg - 1].kind == SEG_MATCH) seg[n_seg - 1].x1 = x1, seg[n_seg - 1].y1 = y1;
+		else if (kind != SEG_NONE) {
+			seg_t *g;
+			if (n_seg == cap_seg) {
+				cap_seg = cap_seg ? cap_seg + (cap_seg >> 1) : 1024;
+				seg = (seg_t*)krealloc(km_tmp, seg, sizeof(seg_t) * (size_t)cap_seg);
+			}
+			g = &seg[n_seg++];
+			g->kind = kind, g->x0 = x0, g->y0 = y0, g->x1 = x1, g->y1 = y1, g->job = job;
+		}
 		x0 = x1, y0 = y1;
 	}
 	{ /* all exact gap fills in one submission (the reference loops over mwf_wfa_exact, :877) */
 		int32_t *jtl = (int32_t*)kmalloc(km_tmp, sizeof(int32_t) * (size_t)(n_job + 1)), *jql = (int32_t*)kmalloc(km_tmp, sizeof(int32_t) * (size_t)(n_job + 1));
 		const char **jts = (const char**)kmalloc(km_tmp, sizeof(char*) * (size_t)(n_job + 1)), **jqs = (const char**)kmalloc(km_tmp, sizeof(char*) * (size_t)(n_job + 1));
 		mwf_rst_t *jr = (mwf_rst_t*)kcalloc(km_tmp, (size_t)(n_job + 1), sizeof(mwf_rst_t));
-		for (i = 0; i <= n_a; ++i)
+		for (i = 0; i < n_seg; ++i)
 			if (seg[i].kind == SEG_EXACT) {
 				const int32_t j = seg[i].job;
 				jtl[j] = seg[i].x1 - seg[i].x0, jts[j] = ts + seg[i].x0;
 				jql[j] = seg[i].y1 - seg[i].y0, jqs[j] = qs + seg[i].y0;
 			}
+		if (timing) t2 = now_ms();
 		if (n_job > 0) mwf_wfa_exact_batch(km_tmp, opt, n_job, jtl, jts, jql, jqs, jr);
-		for (i = 0; i <= n_a; ++i) { /* concatenate in order */
+		if (timing) t3 = now_ms();
+		for (i = 0; i < n_seg; ++i) { /* concatenate in order */
 			const seg_t *g = &seg[i];
 			const int32_t dx = g->x1 - g->x0, dy = g->y1 - g->y0;
 			switch (g->kind) {
@@ -290,4 +389,7 @@ void mwf_wfa_chain(void *km, const mwf_opt_t *opt, int32_t tl, const char *ts, i
 	r->s = score;
 	r->n_cigar = c.n;
 	r->cigar = (uint32_t*)krelocate(km, c.w, sizeof(uint32_t) * (size_t)c.n);
+	if (timing)
+		fprintf(stderr, "[mwf_chain] %d x %d: anchors %.2f ms (%d), classify %.2f ms, %d gap fills %.2f ms, assemble %.2f ms\n",
+		        tl, ql, t1 - t0, n_a, t2 - t1, n_job, t3 - t2, now_ms() - t3);
 }

@@ -993,6 +993,16 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	b->opt = *opt;
 	b->n = n_pairs;
 	b->is_tb = !!(opt->flag & MWF_F_CIGAR);
+	if (b->is_tb && opt->step > 0) {
+		/* The first snapshot of low-memory mode is taken at score opt->step (miniwfa.c:585-586).  When no pair of the batch can
+		 * score that much (deleting one sequence and inserting the other bounds the score), pass 1 finds no checkpoint and
+		 * pass 2 is the high-memory run: skip pass 1.  (The gap fills of mwf_wfa_chain: ~1e5 pairs of a few dozen bases.) */
+		bool reachable = false;
+		for (int i = 0; i < n_pairs && !reachable; ++i)
+			reachable = gap_cost(opt, tl[i]) + gap_cost(opt, ql[i]) >= opt->step;
+		if (!reachable) b->opt.step = 0;
+	}
+	opt = &b->opt;
 	const bool seg = b->is_tb && opt->step > 0;
 	int max_pen = opt->x;
 	max_pen = std::max(max_pen, opt->o1 + opt->e1);
@@ -1133,7 +1143,12 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			double expect = 0;
 			for (int i = 0; i < std::min(wp, n_pairs); ++i) {
 				const double len = std::max(tl[b->order[i]], ql[b->order[i]]);
-				expect += 0.09 * len * len + 4096.0 * len;
+				double e = 0.09 * len * len + 4096.0 * len;
+				/* a max_iter budget (mwf_wfa_auto's first attempt: 1e8 cells) bounds the bytes too: the run stops within one block
+				 * of scores of the budget (pass 1 of low-memory mode has no stop tests) */
+				if (opt->max_iter > 0 && !seg)
+					e = std::min(e, (double)opt->max_iter + (TILE_TMAX + 2.0) * ((double)tl[b->order[i]] + ql[b->order[i]] + 2.0 * n + 2.0 * TILE_TMAX + 16));
+				expect += e;
 			}
 			b->arena_total = (long long)std::min((double)b->arena_full, std::max(expect, 64.0 * 1048576)) & ~255LL;
 			if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) /* tests */
@@ -1513,22 +1528,60 @@ extern "C" void mwf_b200_batch_wait(mwf_b200_batch_t *b)
 	}
 }
 
+/* CIGARs of many pairs: packed back to back on the device (one warp per pair), so that the batch needs one copy to the host
+ * instead of one per pair (~10 us each: 1 s for the 100 000 gap fills of a 5 Mb mwf_wfa_chain) */
+__global__ void __launch_bounds__(256) cigar_gather_kernel(const PairOut *__restrict__ outs, const long long *__restrict__ off,
+                                                           const uint32_t *__restrict__ cigar, uint32_t *__restrict__ dst, int n)
+{
+	const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (w >= n) return;
+	const long long o0 = off[w], cnt = off[w + 1] - o0;
+	if (cnt <= 0) return;
+	const uint32_t *src = cigar + outs[w].cigar_pos;
+	for (long long j = lane; j < cnt; j += 32) dst[o0 + j] = src[j];
+}
+
 extern "C" void mwf_b200_batch_fetch(mwf_b200_batch_t *b, void *km, mwf_rst_t *r)
 {
 	mwf_b200_batch_wait(b);
 	b->d2h = (int64_t)sizeof(PairOut) * b->n;
+	long long total = 0;
+	int with_cigar = 0;
 	for (int i = 0; i < b->n; ++i) {
 		const PairOut &o = b->h_outs[i];
 		r[i].s = o.s, r[i].n_iter = o.n_iter, r[i].n_cigar = 0, r[i].cigar = 0;
 		if (o.s >= 0 && o.n_cigar > 0) {
 			r[i].n_cigar = o.n_cigar;
 			r[i].cigar = (uint32_t*)kmalloc(km, sizeof(uint32_t) * (size_t)o.n_cigar);
-			CUDA_OK(cudaMemcpyAsync(r[i].cigar, b->d_cigar + o.cigar_pos, sizeof(uint32_t) * (size_t)o.n_cigar,
-			                        cudaMemcpyDeviceToHost, b->stream));
-			b->d2h += (int64_t)sizeof(uint32_t) * o.n_cigar;
+			total += o.n_cigar, ++with_cigar;
 		}
 	}
-	CUDA_OK(cudaStreamSynchronize(b->stream));
+	b->d2h += (int64_t)sizeof(uint32_t) * total;
+	if (with_cigar > 8) { /* gather on the device, one copy, scatter on the host */
+		long long *h_off = 0, *d_off = 0;
+		uint32_t *d_all = 0, *h_all = 0;
+		ws_host(&h_off, sizeof(long long) * ((size_t)b->n + 1));
+		ws_dev(&d_off, sizeof(long long) * ((size_t)b->n + 1), b->dev);
+		ws_dev(&d_all, sizeof(uint32_t) * (size_t)total, b->dev);
+		ws_host(&h_all, sizeof(uint32_t) * (size_t)total);
+		h_off[0] = 0;
+		for (int i = 0; i < b->n; ++i) h_off[i + 1] = h_off[i] + r[i].n_cigar;
+		CUDA_OK(cudaMemcpyAsync(d_off, h_off, sizeof(long long) * ((size_t)b->n + 1), cudaMemcpyHostToDevice, b->stream));
+		cigar_gather_kernel<<<(unsigned)(((long long)b->n * 32 + 255) / 256), 256, 0, b->stream>>>(b->d_outs, d_off, b->d_cigar, d_all, b->n);
+		CUDA_OK(cudaGetLastError());
+		++b->launches;
+		CUDA_OK(cudaMemcpyAsync(h_all, d_all, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaStreamSynchronize(b->stream));
+		for (int i = 0; i < b->n; ++i)
+			if (r[i].n_cigar > 0) memcpy(r[i].cigar, h_all + h_off[i], sizeof(uint32_t) * (size_t)r[i].n_cigar);
+		ws_free(h_off); ws_free(d_off); ws_free(d_all); ws_free(h_all);
+	} else if (with_cigar > 0) { /* few (possibly very long) CIGARs: straight into the caller's buffers */
+		for (int i = 0; i < b->n; ++i)
+			if (r[i].n_cigar > 0)
+				CUDA_OK(cudaMemcpyAsync(r[i].cigar, b->d_cigar + b->h_outs[i].cigar_pos, sizeof(uint32_t) * (size_t)r[i].n_cigar,
+				                        cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaStreamSynchronize(b->stream));
+	}
 }
 
 extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
@@ -1564,3 +1617,5 @@ extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pa
 	mwf_b200_batch_fetch(b, km, r);
 	mwf_b200_batch_destroy(b);
 }
+
+#include "kmer_front.cuh"

@@ -209,10 +209,13 @@ def test_batch_object_reuse_and_timers():
         assert b.kernel_ms > 0 and b.launches >= 1 and b.h2d_bytes > 8 * 40000
 
 
-def test_chain_and_auto_golden(golden, golden_chain):
-    """mwf_wfa_chain / mwf_wfa_auto (host chaining + one GPU batch of gap fills) against the reference's own output:
-    score, CIGAR words and the n_iter the reference leaves in the result."""
+@pytest.mark.parametrize("front", ["default", "gpu", "host"])
+def test_chain_and_auto_golden(golden, golden_chain, monkeypatch, front):
+    """mwf_wfa_chain / mwf_wfa_auto (k-mer front end on the device or, for small inputs, the host; LIS on the host; one GPU
+    batch of gap fills) against the reference's own output: score, CIGAR words and the n_iter the reference leaves in the result."""
     mw.set_kernel(mw.KERNEL_AUTO)
+    if front != "default":
+        monkeypatch.setenv("MWF_B200_CHAIN_FRONT", front)
     import ctypes
     L = mw.lib()
     n = 0
@@ -230,6 +233,103 @@ def test_chain_and_auto_golden(golden, golden_chain):
             assert mw.cigar2score(o, cig)[1:] == (len(t), len(q)), c["name"]
         n += 1
     assert n >= 40
+
+
+_NT4 = {ord(c): v for c, v in zip("ACGTUacgtu", (0, 1, 2, 3, 3, 0, 1, 2, 3, 3))}
+_NT4.update({0: 0, 1: 1, 2: 2, 3: 3})
+
+
+def _py_kmers(s, k):
+    """(k-mer word, position of its last base) of every valid k-mer: mg_fc_kmer (miniwfa.c:718-730), plain Python."""
+    out, word, run, mask = [], 0, 0, (1 << 2 * k) - 1
+    for i, ch in enumerate(s):
+        c = _NT4.get(ch, 4)
+        if c < 4:
+            word, run = (word << 2 | c) & mask, run + 1
+            if run >= k:
+                out.append((word, i))
+        else:
+            word, run = 0, 0
+    return out
+
+
+def _py_hits_and_shared(t, q, k, max_occ):
+    from collections import defaultdict
+    dt, dq = defaultdict(list), defaultdict(list)
+    kt, kq = _py_kmers(t, k), _py_kmers(q, k)
+    for w, i in kt:
+        dt[w].append(i)
+    for w, i in kq:
+        dq[w].append(i)
+    hits = sorted((tp, qp) for w, tps in dt.items() if w in dq and len(tps) <= max_occ and len(dq[w]) <= max_occ
+                  for tp in tps for qp in dq[w])
+    shared = sum(min(len(v), len(dq[w])) for w, v in dt.items() if w in dq)
+    return [qp << 32 | tp for tp, qp in hits], (len(kt), len(kq), shared)
+
+
+def test_kmer_front_end_against_python_restatement():
+    """mwf_b200_kmer_hits / mwf_b200_kmer_shared (list, sort, match, sort on the device) against a plain-Python restatement
+    of mg_fc_kmer + the match loop of mg_chain (miniwfa.c:718-770) and of mwf_ksim's counts (:786-812): soft-masked and
+    N-containing sequences, raw 0..3 codes, homopolymer runs (large groups), every k from 2 to 15, several max_occ."""
+    rng = random.Random(99)
+
+    def mutate(s, p):
+        out = bytearray()
+        for ch in s:
+            r = rng.random()
+            if r < p * 0.4:
+                continue
+            if r < p * 0.8:
+                out.append(rng.choice(b"ACGT"))
+            out.append(ch)
+        return bytes(out)
+
+    cases = []
+    for k in range(2, 16):
+        n = 200 if k < 5 else 6000
+        t = bytes(rng.choice(b"ACGT") for _ in range(n))
+        cases.append((t, mutate(t, 0.05), k, rng.choice((1, 2, 3, 50))))
+    t = bytes(rng.choice(b"ACGTacgtNnU") for _ in range(20000))
+    cases.append((t, mutate(t, 0.03), 13, 2))
+    cases.append((t, mutate(t, 0.03), 7, 4))
+    t = bytes(rng.choice((0, 1, 2, 3)) for _ in range(5000))  # raw codes
+    cases.append((t, mutate(t, 0.02), 11, 2))
+    t = b"A" * 3000 + bytes(rng.choice(b"ACGT") for _ in range(3000)) + b"CA" * 1500 + b"T" * 5  # huge groups
+    cases.append((t, mutate(t, 0.02), 13, 2))
+    cases.append((t, mutate(t, 0.02), 4, 3000))
+    cases.append((b"ACGTACGTACGTAC", b"ACGTACGTACGTAC", 13, 2))   # two k-mers each
+    cases.append((b"ACGTACGTACGTA", b"NNNNNNNNNNNNNNNN", 13, 2))    # nothing valid in the query
+    cases.append((b"ACGTACGTACGT", b"ACGTACGTACGTACGT", 13, 2))    # target shorter than k
+    t = bytes(rng.choice(b"ACGT") for _ in range(70000))              # many tiles, more than one sort pass
+    cases.append((t, mutate(t, 0.05), 13, 2))
+    for t, q, k, occ in cases:
+        hits, counts = _py_hits_and_shared(t, q, k, occ)
+        assert mw.kmer_hits(t, q, k, occ) == hits, (len(t), len(q), k, occ)
+        if len(t) >= k and len(q) >= k:
+            assert mw.kmer_shared(t, q, k) == counts, (len(t), len(q), k)
+    assert mw.lib().mwf_b200_kmer_launches() > 0
+
+
+@pytest.mark.parametrize("n,p,flag", [(300000, 0.03, 1), (1000000, 0.03, 0)])
+def test_chain_large_pair_against_reference(n, p, flag):
+    """mwf_wfa_chain on pairs large enough for the device front end and tens of thousands of gap fills, against the
+    unmodified reference (oracle/_ref) on the same input; plus a long unrelated insert so that mwf_ksim's branch runs."""
+    ref = orc.reference()
+    if ref is None:
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    import ctypes
+    t, q = synth.make_pair(n, p, 7)
+    junk = synth.make_pair(15000, 0.0, 8)[0]
+    t = t[:n // 2] + synth.make_pair(12000, 0.0, 9)[0] + t[n // 2:]
+    q = q[:len(q) // 2] + junk + q[len(q) // 2:]
+    o = mw.opt_init(flag=flag, step=5000 if flag else 0)
+    r = mw.wfa_chain(o, t, q)
+    ro, rr = orc.make_opt(flag=flag, step=5000 if flag else 0), orc.Rst()
+    ref.mwf_wfa_chain(None, ctypes.byref(ro), len(t), t, len(q), q, ctypes.byref(rr))
+    assert (r[0], r[1]) == (rr.s, rr.n_cigar)
+    assert r[3] == [rr.cigar[i] for i in range(rr.n_cigar)]
+    if flag:
+        assert mw.cigar2score(o, r[3])[1:] == (len(t), len(q))
 
 
 def test_cli_matches_reference_output(tmp_path):
