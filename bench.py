@@ -397,6 +397,35 @@ def main():
                            "value": max(len(t), len(q)) * rl[0] / dt, "unit": UNIT,
                            "check": "CIGAR re-scored with mwf_cigar2score: score == s and it consumes both sequences"}
             del t, q
+        # mwf_wfa_auto on the config-5 pair: exact with a budget of 1e8 cells, then the chaining heuristic (k-mer front end on
+        # the device, all gap fills as one batch); the unmodified reference's mwf_wfa_auto on one host core beside it
+        t, q = synth.make_pair(5000000, 0.03, 424242)
+        oa = mw.opt_init(flag=mw.F_CIGAR)
+        k0 = int(mw.lib().mwf_b200_kmer_launches())
+        ta = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ra = mw.wfa_auto(oa, t, q)
+            ta.append(time.perf_counter() - t0)
+        assert mw.cigar2score(oa, ra[3])[1:] == (len(t), len(q))
+        auto = {"workload": "mwf_wfa_auto (miniwfa.c:898-908) on the config-5 pair, CIGAR: host buffers in, CIGAR out", "s": ra[0],
+                "n_cigar": ra[1], "seconds_first_call": ta[0], "seconds": min(ta[1:]),
+                "kmer_front_end_launches_per_call": (int(mw.lib().mwf_b200_kmer_launches()) - k0) // 3}
+        if not args.no_cpu:
+            try:
+                from oracle import orc
+                ref = orc.reference()
+            except Exception:
+                ref = None
+            if ref is not None:
+                ro, rr = orc.make_opt(flag=1), orc.Rst()
+                t0 = time.perf_counter()
+                ref.mwf_wfa_auto(None, ctypes.byref(ro), len(t), t, len(q), q, ctypes.byref(rr))
+                auto["reference_cpu_seconds"] = time.perf_counter() - t0
+                auto["check"] = "score and all CIGAR words equal to the reference's"
+                assert (rr.s, rr.n_cigar) == (ra[0], ra[1]) and rr.cigar[:rr.n_cigar] == ra[3]
+        large["auto"] = auto
+        del t, q
         large["reference_published"] = "README.md:98-99 (Xeon 6230, 1 thread): MHC (s = 229 868) 385 s high-memory / 544 s low-memory"
         line["large_pairs"] = large
         mw.lib().mwf_b200_release_cache()
