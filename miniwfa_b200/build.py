@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
         objs.append(o)
     _run([_nvcc(), "-shared", "-o", OUT] + objs + ["-Xcompiler", "-fPIC", "-lpthread"])
     if os.path.exists(cli_src):
-        _run(["gcc"] + CC_FLAGS + [cli_src, "-o", CLI, "-L", HERE, "-lminiwfa_b200", "-Wl,-rpath,$ORIGIN", "-lz"])
+        _run(["gcc"] + CC_FLAGS + [cli_src, "-o", CLI, "-L", HERE, "-lminiwfa_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"])
     return OUT
 
 

@@ -3,9 +3,10 @@
  *
  * Same options (-c -p INT -u -t -l INT -f INT -a -e -K -d, reference main.c:29-39), same pairing of the i-th
  * records of the two files (main.c:67), same PAF-like output line and CIGAR (main.c:73-80), and mwf_assert_cigar
- * on every CIGAR (main.c:72).  Different on purpose: in exact mode all pairs of the two files are read first and
- * submitted as ONE batch (mwf_wfa_exact_batch), because one submission keeps every SM busy; the "T" lines on
- * stderr therefore report wall-clock seconds of the whole batch divided by the number of pairs.
+ * on every CIGAR (main.c:72).  Different on purpose: in exact mode the pairs are submitted in batches
+ * (mwf_wfa_exact_batch), because one submission of many pairs keeps every SM busy, and a reader thread parses the next
+ * chunk of both files (256 Mbases or 65 536 pairs; MWF_CLI_CHUNK_BASES / MWF_CLI_CHUNK_PAIRS) while the GPU works on the
+ * current one; the "T" lines on stderr therefore report wall-clock seconds of a batch divided by its number of pairs.
  * Input: FASTA or 4-line FASTQ, plain or gzip (zlib), one sequence per record, multi-line FASTA accepted.
  */
 #include <stdio.h>
@@ -14,11 +15,11 @@
 #include <unistd.h>
 #include <time.h>
 #include <zlib.h>
+#include <pthread.h>
 #include "miniwfa.h"
 #include "mwf_b200.h"
 
 typedef struct { char *name, *seq; int32_t len; } rec_t;
-typedef struct { rec_t *a; int n, cap; } recs_t;
 
 static void *xrealloc(void *p, size_t n)
 {
@@ -43,41 +44,130 @@ static int read_line(gzFile fp, char **buf, size_t *cap) /* one line without its
 	return (int)len;
 }
 
-static void read_records(const char *path, recs_t *out)
+/* incremental FASTA / FASTQ reader: one record per call */
+typedef struct {
+	gzFile fp;
+	char *line;
+	size_t cap;
+	int n, pending, fastq; /* pending: `line` holds a header line that has not been consumed yet */
+} reader_t;
+
+static void reader_open(reader_t *r, const char *path)
 {
-	gzFile fp = strcmp(path, "-") ? gzopen(path, "r") : gzdopen(0, "r");
-	char *line = 0, *seq = 0;
-	size_t cap = 0, scap = 0, slen = 0;
-	int n, fastq = 0, have = 0, in_qual = 0;
-	size_t qual_left = 0;
-	if (fp == 0) { fprintf(stderr, "ERROR: cannot open %s\n", path); exit(1); }
-	out->a = 0, out->n = out->cap = 0;
-	while ((n = read_line(fp, &line, &cap)) >= 0) {
+	memset(r, 0, sizeof(*r));
+	r->fp = strcmp(path, "-") ? gzopen(path, "r") : gzdopen(0, "r");
+	if (r->fp == 0) { fprintf(stderr, "ERROR: cannot open %s\n", path); exit(1); }
+	gzbuffer(r->fp, 1 << 20);
+}
+
+static void reader_close(reader_t *r) { free(r->line); gzclose(r->fp); }
+
+static int is_header(const reader_t *r, int n, int have)
+{
+	return n > 0 && (r->line[0] == '>' || (r->line[0] == '@' && (!have || r->fastq)));
+}
+
+static int next_record(reader_t *r, rec_t *out) /* 1 = a record, 0 = end of file */
+{
+	char *seq = 0, *sp;
+	size_t scap = 0, slen = 0, qual_left = 0;
+	int in_qual = 0;
+	if (!r->pending) { /* skip to the first header */
+		while ((r->n = read_line(r->fp, &r->line, &r->cap)) >= 0 && !is_header(r, r->n, 0)) {}
+		if (r->n < 0) return 0;
+	}
+	r->pending = 0;
+	r->fastq = r->line[0] == '@';
+	for (sp = r->line + 1; *sp && *sp != ' ' && *sp != '\t'; ++sp) {}
+	*sp = 0;
+	out->name = strdup(r->line + 1);
+	while ((r->n = read_line(r->fp, &r->line, &r->cap)) >= 0) {
+		const int n = r->n;
 		if (in_qual) { /* FASTQ quality: as many characters as bases */
 			qual_left = qual_left > (size_t)n ? qual_left - (size_t)n : 0;
 			if (qual_left == 0) in_qual = 0;
 			continue;
 		}
-		if (n > 0 && (line[0] == '>' || (line[0] == '@' && (!have || fastq)))) {
-			char *sp;
-			if (have) { out->a[out->n - 1].seq = (char*)xrealloc(seq, slen + 1), out->a[out->n - 1].seq[slen] = 0, out->a[out->n - 1].len = (int32_t)slen; }
-			fastq = line[0] == '@';
-			if (out->n == out->cap) out->cap = out->cap ? out->cap * 2 : 16, out->a = (rec_t*)xrealloc(out->a, sizeof(rec_t) * out->cap);
-			for (sp = line + 1; *sp && *sp != ' ' && *sp != '\t'; ++sp) {}
-			*sp = 0;
-			out->a[out->n].name = strdup(line + 1), out->a[out->n].seq = 0, out->a[out->n].len = 0;
-			++out->n, have = 1;
-			seq = 0, scap = slen = 0;
-		} else if (have && fastq && n > 0 && line[0] == '+') {
-			in_qual = slen > 0, qual_left = slen;
-		} else if (have) {
+		if (is_header(r, n, 1)) { r->pending = 1; break; }
+		if (r->fastq && n > 0 && r->line[0] == '+') in_qual = slen > 0, qual_left = slen;
+		else {
 			if (slen + n + 1 > scap) scap = (slen + n + 1) * 2, seq = (char*)xrealloc(seq, scap);
-			memcpy(seq + slen, line, n), slen += n;
+			memcpy(seq + slen, r->line, n), slen += n;
 		}
 	}
-	if (have) { out->a[out->n - 1].seq = (char*)xrealloc(seq, slen + 1), out->a[out->n - 1].seq[slen] = 0, out->a[out->n - 1].len = (int32_t)slen; }
-	free(line);
-	gzclose(fp);
+	out->seq = (char*)xrealloc(seq, slen + 1), out->seq[slen] = 0, out->len = (int32_t)slen;
+	return 1;
+}
+
+/*
+ * Ingest pipeline: a reader thread parses the i-th records of both files into chunks of pairs (bounded by
+ * bases and by pairs) while the main thread aligns the previous chunk on the GPU and prints it; at most two chunks wait in the
+ * queue, so host memory stays bounded on files of any size.  Inside a chunk the library stages the sequences through pinned
+ * memory (mwf_b200_batch_upload).
+ */
+typedef struct chunk_s { rec_t *t, *q; int n; struct chunk_s *next; } chunk_t;
+
+typedef struct {
+	const char *path[2];
+	long long max_bases;
+	int max_pairs;
+	pthread_mutex_t mu;
+	pthread_cond_t cv;
+	chunk_t *head, *tail;
+	int n_queued, done;
+} ingest_t;
+
+static void *ingest_main(void *arg)
+{
+	ingest_t *g = (ingest_t*)arg;
+	reader_t r1, r2;
+	int eof = 0;
+	reader_open(&r1, g->path[0]);
+	reader_open(&r2, g->path[1]);
+	while (!eof) {
+		chunk_t *c = (chunk_t*)calloc(1, sizeof(chunk_t));
+		long long bases = 0;
+		int cap = 0;
+		while (c->n < g->max_pairs && bases < g->max_bases) {
+			rec_t a, b;
+			if (!next_record(&r1, &a)) { eof = 1; break; }
+			if (!next_record(&r2, &b)) { free(a.name); free(a.seq); eof = 1; break; }
+			if (c->n == cap) {
+				cap = cap ? cap * 2 : 64;
+				c->t = (rec_t*)xrealloc(c->t, sizeof(rec_t) * cap), c->q = (rec_t*)xrealloc(c->q, sizeof(rec_t) * cap);
+			}
+			c->t[c->n] = a, c->q[c->n] = b, ++c->n;
+			bases += (long long)a.len + b.len;
+		}
+		pthread_mutex_lock(&g->mu);
+		while (g->n_queued >= 2) pthread_cond_wait(&g->cv, &g->mu);
+		if (c->n > 0) {
+			if (g->tail) g->tail->next = c; else g->head = c;
+			g->tail = c, ++g->n_queued;
+		} else free(c);
+		if (eof) g->done = 1;
+		pthread_cond_broadcast(&g->cv);
+		pthread_mutex_unlock(&g->mu);
+	}
+	reader_close(&r1);
+	reader_close(&r2);
+	return 0;
+}
+
+static chunk_t *ingest_pop(ingest_t *g) /* NULL after the last chunk */
+{
+	chunk_t *c;
+	pthread_mutex_lock(&g->mu);
+	while (g->head == 0 && !g->done) pthread_cond_wait(&g->cv, &g->mu);
+	c = g->head;
+	if (c) {
+		g->head = c->next;
+		if (g->head == 0) g->tail = 0;
+		--g->n_queued;
+		pthread_cond_broadcast(&g->cv);
+	}
+	pthread_mutex_unlock(&g->mu);
+	return c;
 }
 
 static double wall(void)
@@ -103,7 +193,9 @@ static void print_pair(const mwf_opt_t *opt, const rec_t *t, const rec_t *q, con
 int main(int argc, char *argv[])
 {
 	mwf_opt_t opt;
-	recs_t f1, f2;
+	ingest_t ing;
+	chunk_t *ck;
+	pthread_t tid;
 	mwf_rst_t *rst;
 	int c, mode = 0, n, i;
 	double t0, dt;
@@ -138,31 +230,40 @@ int main(int argc, char *argv[])
 		fprintf(stderr, "  -K       disable the kalloc allocator\n");
 		return 1;
 	}
-	read_records(argv[optind], &f1);
-	read_records(argv[optind + 1], &f2);
-	n = f1.n < f2.n ? f1.n : f2.n;
-	rst = (mwf_rst_t*)calloc(n > 0 ? n : 1, sizeof(mwf_rst_t));
-	t0 = wall();
-	if (mode == 0) { /* every pair of the two files in one submission */
-		int32_t *tl = (int32_t*)malloc(sizeof(int32_t) * (n + 1)), *ql = (int32_t*)malloc(sizeof(int32_t) * (n + 1));
-		const char **ts = (const char**)malloc(sizeof(char*) * (n + 1)), **qs = (const char**)malloc(sizeof(char*) * (n + 1));
-		for (i = 0; i < n; ++i) tl[i] = f1.a[i].len, ts[i] = f1.a[i].seq, ql[i] = f2.a[i].len, qs[i] = f2.a[i].seq;
-		mwf_wfa_exact_batch(0, &opt, n, tl, ts, ql, qs, rst);
-		free(tl); free(ql); free((void*)ts); free((void*)qs);
-	} else {
-		for (i = 0; i < n; ++i) {
-			if (mode == 1) mwf_wfa_chain(0, &opt, f1.a[i].len, f1.a[i].seq, f2.a[i].len, f2.a[i].seq, &rst[i]);
-			else mwf_wfa_auto(0, &opt, f1.a[i].len, f1.a[i].seq, f2.a[i].len, f2.a[i].seq, &rst[i]);
+	memset(&ing, 0, sizeof(ing));
+	ing.path[0] = argv[optind], ing.path[1] = argv[optind + 1];
+	ing.max_bases = getenv("MWF_CLI_CHUNK_BASES") ? atoll(getenv("MWF_CLI_CHUNK_BASES")) : 256LL << 20;
+	ing.max_pairs = getenv("MWF_CLI_CHUNK_PAIRS") ? atoi(getenv("MWF_CLI_CHUNK_PAIRS")) : 65536;
+	if (ing.max_bases < 1) ing.max_bases = 1;
+	if (ing.max_pairs < 1) ing.max_pairs = 1;
+	pthread_mutex_init(&ing.mu, 0);
+	pthread_cond_init(&ing.cv, 0);
+	if (pthread_create(&tid, 0, ingest_main, &ing) != 0) { fprintf(stderr, "ERROR: cannot start the reader thread\n"); return 1; }
+	while ((ck = ingest_pop(&ing)) != 0) {
+		n = ck->n;
+		rst = (mwf_rst_t*)calloc(n, sizeof(mwf_rst_t));
+		t0 = wall();
+		if (mode == 0) { /* every pair of the chunk in one submission */
+			int32_t *tl = (int32_t*)malloc(sizeof(int32_t) * n), *ql = (int32_t*)malloc(sizeof(int32_t) * n);
+			const char **ts = (const char**)malloc(sizeof(char*) * n), **qs = (const char**)malloc(sizeof(char*) * n);
+			for (i = 0; i < n; ++i) tl[i] = ck->t[i].len, ts[i] = ck->t[i].seq, ql[i] = ck->q[i].len, qs[i] = ck->q[i].seq;
+			mwf_wfa_exact_batch(0, &opt, n, tl, ts, ql, qs, rst);
+			free(tl); free(ql); free((void*)ts); free((void*)qs);
+		} else {
+			for (i = 0; i < n; ++i) {
+				if (mode == 1) mwf_wfa_chain(0, &opt, ck->t[i].len, ck->t[i].seq, ck->q[i].len, ck->q[i].seq, &rst[i]);
+				else mwf_wfa_auto(0, &opt, ck->t[i].len, ck->t[i].seq, ck->q[i].len, ck->q[i].seq, &rst[i]);
+			}
 		}
+		dt = wall() - t0;
+		for (i = 0; i < n; ++i) {
+			print_pair(&opt, &ck->t[i], &ck->q[i], &rst[i]);
+			free(rst[i].cigar);
+			fprintf(stderr, "T\t%s\t%s\t%.3f\n", ck->t[i].name, ck->q[i].name, dt / n);
+			free(ck->t[i].name); free(ck->t[i].seq); free(ck->q[i].name); free(ck->q[i].seq);
+		}
+		free(ck->t); free(ck->q); free(ck); free(rst);
 	}
-	dt = wall() - t0;
-	for (i = 0; i < n; ++i) {
-		print_pair(&opt, &f1.a[i], &f2.a[i], &rst[i]);
-		free(rst[i].cigar);
-		fprintf(stderr, "T\t%s\t%s\t%.3f\n", f1.a[i].name, f2.a[i].name, dt / n);
-	}
-	for (i = 0; i < f1.n; ++i) free(f1.a[i].name), free(f1.a[i].seq);
-	for (i = 0; i < f2.n; ++i) free(f2.a[i].name), free(f2.a[i].seq);
-	free(f1.a); free(f2.a); free(rst);
+	pthread_join(tid, 0);
 	return 0;
 }

@@ -112,7 +112,7 @@ static void sort64(void *km, uint64_t *a, size_t n)
 	kfree(km, tmp);
 }
 
-/* longest strictly increasing subsequence of v[0..n); writes the chosen indices to pick[], returns their number (:678-697).
+/* longest strictly increasing subsequence of v[0..n): returns its *n_out values in a kmalloc'ed array (:678-697, :772-774).
  * tailv[l] / tail[l] = value / index of the smallest last element of an increasing chain of length l (tailv is strictly
  * increasing in l).  An element x goes behind the longest chain whose last value is below it, lo = max { l : tailv[l] < x }.
  * On similar sequences that chain is nearly always among the longest few, so the search first gallops down from the top; a
@@ -120,11 +120,13 @@ static void sort64(void *km, uint64_t *a, size_t n)
  * a dozen cache misses -- those go through samp[b] = tailv[64 b], which stays in cache, and then one 64-entry block.
  * Same lo as plain bisection, so the same chain as the reference's mg_lis_64. */
 #define LIS_BLK 64
+#define LIS_AHEAD 16
 
-static int32_t longest_increasing(void *km, int32_t n, const uint64_t *v, int32_t *pick)
+static uint64_t *longest_increasing(void *km, int32_t n, const uint64_t *v, int32_t *n_out)
 {
 	int32_t *tail, *prev, i, len = 0, at;
-	uint64_t *tailv, *samp;
+	uint64_t *tailv, *samp, *out;
+	*n_out = 0;
 	if (n <= 0) return 0;
 	tail = (int32_t*)kmalloc(km, sizeof(int32_t) * ((size_t)n + 1));
 	tailv = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)n + 1));
@@ -133,6 +135,18 @@ static int32_t longest_increasing(void *km, int32_t n, const uint64_t *v, int32_
 	for (i = 0; i < n; ++i) {
 		const uint64_t x = v[i];
 		int32_t lo = len;
+		if (i + LIS_AHEAD < n && len >= 4 * LIS_BLK) { /* a stray match a few elements ahead: fetch the block it will land in */
+			const uint64_t y = v[i + LIS_AHEAD];
+			if (tailv[len - LIS_BLK] >= y) {
+				int32_t bl = 0, bh = len / LIS_BLK + 1;
+				while (bh - bl > 1) {
+					const int32_t bm = bl + ((bh - bl) >> 1);
+					if (samp[bm] < y) bl = bm; else bh = bm;
+				}
+				__builtin_prefetch(&tailv[bl * LIS_BLK + LIS_BLK / 4]), __builtin_prefetch(&tailv[bl * LIS_BLK + 3 * LIS_BLK / 4]);
+				__builtin_prefetch(&tail[bl * LIS_BLK + LIS_BLK / 4]), __builtin_prefetch(&tail[bl * LIS_BLK + 3 * LIS_BLK / 4]);
+			}
+		}
 		if (len > 0 && tailv[len] >= x) {
 			int32_t hi = len, step = 1; /* invariant: tailv[hi] >= x */
 			lo = hi - 1;
@@ -158,12 +172,14 @@ static int32_t longest_increasing(void *km, int32_t n, const uint64_t *v, int32_
 		if ((lo + 1) % LIS_BLK == 0) samp[(lo + 1) / LIS_BLK] = x;
 		if (lo + 1 > len) len = lo + 1;
 	}
-	for (i = len - 1, at = tail[len]; i >= 0; --i) pick[i] = at, at = prev[at];
+	out = (uint64_t*)kmalloc(km, sizeof(uint64_t) * (size_t)len);
+	for (i = len - 1, at = tail[len]; i >= 0; --i) out[i] = v[at], at = prev[at];
 	kfree(km, prev);
 	kfree(km, samp);
 	kfree(km, tailv);
 	kfree(km, tail);
-	return len;
+	*n_out = len;
+	return out;
 }
 
 /* Where the k-mer lists are built, sorted and matched: on the device (kmer_front.cuh) from FRONT_MIN_BASES bases up, on the
@@ -217,7 +233,7 @@ static uint64_t *chain_anchors(void *km, int32_t tl, const char *ts, int32_t ql,
 	const double t0 = timing ? now_ms() : 0;
 	double t1 = 0;
 	uint64_t *hit = 0, *anchors;
-	int32_t n_hit = 0, i, *pick, n_pick;
+	int32_t n_hit = 0, i, n_pick = 0;
 	*n_out = 0;
 	if (tl < k || ql < k) return 0;
 	assert(k >= 2 && k <= 15);
@@ -227,11 +243,9 @@ static uint64_t *chain_anchors(void *km, int32_t tl, const char *ts, int32_t ql,
 		n_hit = (int32_t)n;
 	} else hit = host_hits(km, tl, ts, ql, qs, k, max_occ, &n_hit);
 	if (timing) t1 = now_ms();
-	pick = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)(n_hit > 0 ? n_hit : 1));
-	n_pick = longest_increasing(km, n_hit, hit, pick);
-	anchors = (uint64_t*)kmalloc(km, sizeof(uint64_t) * (size_t)(n_pick > 0 ? n_pick : 1));
-	for (i = 0; i < n_pick; ++i) anchors[i] = hit[pick[i]] >> 32 | hit[pick[i]] << 32;
-	kfree(km, pick);
+	anchors = longest_increasing(km, n_hit, hit, &n_pick);
+	if (anchors == 0) anchors = (uint64_t*)kmalloc(km, sizeof(uint64_t));
+	for (i = 0; i < n_pick; ++i) anchors[i] = anchors[i] >> 32 | anchors[i] << 32; /* back to target << 32 | query (:781-782) */
 	if (on_device) mwf_b200_kmer_free(hit);
 	else kfree(km, hit);
 	*n_out = n_pick;

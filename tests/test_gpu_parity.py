@@ -351,10 +351,12 @@ def test_cli_matches_reference_output(tmp_path):
             "-ct": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t155\t1X16=1X14=128I4=1X24="],
             "-ca": ["t3-0\t61\t0\t61\t+\tt3-1\t189\t0\t189\t272\t1X16=1X18=118I1=10I24="]}
     for flags, lines in want.items():
-        out = subprocess.run([exe] + ([flags] if flags else []) + [str(f1), str(f2)], capture_output=True, text=True, timeout=120)
-        assert out.returncode == 0, out.stderr
-        got = out.stdout.strip().split("\n")
-        assert got[:len(lines)] == lines, (flags, got)
+        for env in ({}, {"MWF_CLI_CHUNK_PAIRS": "1"}):  # one batch for the file; one batch per pair (reader thread ahead of the GPU)
+            out = subprocess.run([exe] + ([flags] if flags else []) + [str(f1), str(f2)], capture_output=True, text=True, timeout=120,
+                                 env=dict(os.environ, **env))
+            assert out.returncode == 0, out.stderr
+            got = out.stdout.strip().split("\n")
+            assert got[:len(lines)] == lines, (flags, env, got)
 
 
 def test_tile_geometry_variants(monkeypatch):
