@@ -941,7 +941,21 @@ static void alloc_streaming(mwf_b200_batch_t *b)
 	const int n = b->pen.nring;
 	const bool seg = b->is_tb && opt->step > 0;
 	const long long max_len = b->max_len, max_sbound = b->max_sbound;
-	b->n_slots = b->kernel == MWF_B200_KERNEL_GRID ? 1 : std::max(1, std::min(b->n, b->n_sm));
+	b->n_slots = 1;
+	if (b->kernel == MWF_B200_KERNEL_CTA) {
+		/* One CTA per pair in flight.  A band is at most tl + ql + 1 diagonals wide: short pairs (the gap fills of mwf_wfa_chain,
+		 * read-sized pairs) get small CTAs, and as many of them per SM as registers allow -- 148 pairs in flight with 512-thread
+		 * CTAs leave the GPU waiting on barriers and L2 round trips. */
+		if (g_threads <= 0 && getenv("MWF_B200_THREADS") == 0) {
+			int t = max_len <= 512 ? 64 : max_len <= 2048 ? 128 : max_len <= 4096 ? 256 : 512;
+			while (t < 512 && (long long)b->n_sm * (512 / t) > 2LL * b->n) t *= 2; /* too few pairs for that many CTAs: larger ones */
+			b->threads = t;
+		}
+		int per_sm = 1;
+		CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wfa_cta_kernel, b->threads, sizeof(int) * (8 + 2 * (size_t)n)));
+		per_sm = std::max(1, std::min(per_sm, env_int("MWF_B200_CTA_PER_SM", 16)));
+		b->n_slots = std::max(1, (int)std::min<long long>(b->n, (long long)b->n_sm * per_sm));
+	}
 	b->pitch = (int)((max_len + 2LL * n + 1 + 24 + 31) & ~31LL);
 	b->ring_stride = (long long)n * 5 * b->pitch;
 	ws_dev(&b->d_ring, sizeof(int32_t) * b->ring_stride * b->n_slots, b->dev);

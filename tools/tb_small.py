@@ -43,3 +43,27 @@ for name, kw in (("score", {}), ("cigar", {"flag": 1}), ("cigar step=5000", {"fl
         d = [(tm[i + 1] - tm[i]) * 1e3 for i in range(5)]
         print("%-16s rep %d: create %.1f upload %.1f run %.1f (kernel %.1f ms, %d launches, kernel %d) fetch %.1f destroy %.1f ms; sum s = %d"
               % (name, rep, d[0], d[1], d[2], kms, launches, used, d[3], d[4], sum(r[i].s for i in range(b.n))), flush=True)
+
+# read-sized pairs: 150 bp, ~2 % differences
+pairs = []
+for i in range(n):
+    t = bytes(rng.choice(b"ACGT") for _ in range(150))
+    q = bytearray(t)
+    for _ in range(3):
+        q[rng.randrange(len(q))] = rng.choice(b"ACGT")
+    pairs.append((t, bytes(q)))
+arrays = mw.api.host_arrays(pairs)
+for name, kw in (("150 bp score", {}), ("150 bp cigar", {"flag": 1})):
+    o = mw.opt_init(**kw)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        with mw.Batch(o, pairs, arrays) as b:
+            b.upload(); b.run(); b.wait()
+            kms = b.kernel_ms
+            r = (mw.MwfRst * b.n)()
+            mw.lib().mwf_b200_batch_fetch(b.h, None, r)
+        dt = time.perf_counter() - t0
+        for i in range(n):
+            if r[i].cigar:
+                mw.lib().kfree(None, r[i].cigar)
+        print("%-16s rep %d: %d pairs, kernel %.2f ms, end to end %.1f ms = %.2f M pairs/s" % (name, rep, n, kms, dt * 1e3, n / dt / 1e6), flush=True)
