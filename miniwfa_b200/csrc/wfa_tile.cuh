@@ -870,7 +870,7 @@ __global__ void wfa_tile_traceback_kernel(const TParams P)
 	Job J;
 	J.tl = pd.tl, J.ql = pd.ql, J.doff = tile_doff(P, pd.tl);
 	J.T8 = P.seq + pd.t_off, J.Q8 = P.seq + pd.q_off;
-	J.arena = P.arena;
+	J.arena = P.arena, J.arena_cap = P.arena_cap;
 	J.rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
 	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap);
 	if (threadIdx.x == 0) {
