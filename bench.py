@@ -380,8 +380,8 @@ def main():
                                    "BASELINE config 4 surrogate: one synthetic 5 Mb pair (p=0.0097, s ~ 231 k), low-memory mode -cp5000"),
                                   ("config5", 0.03, {"flag": mw.F_CIGAR},
                                    "BASELINE config 5 surrogate: one synthetic 5 Mb pair (p=0.03, s ~ 711 k, 5e11 cells), high-memory "
-                                   "CIGAR; its 505 GB of traceback bytes do not fit HBM, so the engine falls back to the segmented "
-                                   "traceback (snapshots + recompute) after the all-at-once attempt runs out of arena")):
+                                   "CIGAR; its 505 GB of traceback bytes do not fit HBM -- predicted from the shared 13-mer fraction of the pair before "
+                                   "any alignment work -- so the engine goes straight to the segmented traceback (snapshots + recompute)")):
             t, q = synth.make_pair(5000000, p, 424242)
             oo = mw.opt_init(**kw)
             with mw.Batch(oo, [(t, q)]) as lb:

@@ -33,6 +33,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <algorithm>
 #include <vector>
 #include <atomic>
@@ -1492,6 +1493,28 @@ static bool grow_arena(mwf_b200_batch_t *b)
 	return true;
 }
 
+/* High-memory CIGAR of a few very long pairs: will the s^2 traceback bytes overflow everything that is free?  The all-at-once
+ * attempt finds out the hard way (1.5 s on a 5 Mb pair at 3 %, all of it thrown away); the fraction f of shared 13-mers tells
+ * beforehand (3 ms, kmer_front.cuh): f ~ (1 - p)^13 for a per-base difference rate p, s >~ 0.8 x p n (every difference costs
+ * at least about a mismatch; 0.8 leaves room for the estimate), and the bytes are ~ s^2.  A wrong guess only costs time -- both
+ * routes give the same CIGAR -- so the test is one-sided: skip the attempt only when the low estimate already overflows. */
+static bool predict_arena_overflow(const mwf_b200_batch_t *b)
+{
+	if (!env_int("MWF_B200_TILE_PREDICT", 1) || b->n > 8 || b->max_len < env_int("MWF_B200_TILE_PREDICT_MINLEN", 2000000)) return false;
+	double bytes = 0;
+	for (int i = 0; i < b->n; ++i) {
+		const PairDesc &p = b->pairs[i];
+		int64_t n1 = 0, n2 = 0, shared = 0;
+		if (p.tl < 13 || p.ql < 13) continue;
+		mwf_b200_kmer_shared(p.tl, (const char*)b->h_seq + p.t_off, p.ql, (const char*)b->h_seq + p.q_off, 13, &n1, &n2, &shared);
+		const double f = std::min(n1, n2) > 0 ? (double)shared / (double)std::min(n1, n2) : 0.0;
+		const double diff = 1.0 - pow(std::min(1.0, std::max(f, 1e-9)), 1.0 / 13.0);
+		const double s_low = 0.8 * b->opt.x * diff * std::max(p.tl, p.ql) + gap_cost(&b->opt, p.tl > p.ql ? p.tl - p.ql : p.ql - p.tl);
+		bytes += s_low * s_low;
+	}
+	return bytes > (double)b->arena_full;
+}
+
 extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 {
 	CUDA_OK(cudaSetDevice(b->dev));
@@ -1500,6 +1523,7 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 	if (b->n > 0) {
 		if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb && b->opt.step <= 0) { /* high-memory CIGAR */
 			bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
+			if (!segmented && b->arena_total >= b->arena_full && predict_arena_overflow(b)) segmented = true;
 			while (!segmented) { /* optimistic: all s^2 traceback bytes at once */
 				if (run_tile(b)) break;
 				if (!grow_arena(b)) segmented = true;

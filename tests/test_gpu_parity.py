@@ -436,6 +436,30 @@ def test_segmented_traceback(monkeypatch):
         assert mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR), t, q) == w
 
 
+def test_arena_overflow_predicted_from_shared_kmers(monkeypatch):
+    """A few very long pairs whose s^2 traceback bytes cannot fit skip the all-at-once attempt: the shared 13-mer fraction
+    (mwf_b200_kmer_shared) gives a low estimate of s beforehand.  Forced here on a 12 kb pair with a 300 kB arena: the launch
+    count shows that no all-at-once attempt ran, the CIGAR is the reference's; a near-identical pair is not predicted to overflow."""
+    mw.set_kernel(mw.KERNEL_TILE)
+    monkeypatch.setenv("MWF_B200_TILE_PREDICT_MINLEN", "1000")
+    monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", "300000")
+    rng = random.Random(5)
+    t = bytes(rng.choice(b"ACGT") for _ in range(12000))
+    o = mw.opt_init(flag=mw.F_CIGAR)
+    launches = {}
+    for name, q in (("far", mutate(rng, t, 0.1)), ("near", mutate(rng, t, 0.002))):
+        want = orc.checker_exact(orc.make_opt(flag=1), t, q)
+        for predict in ("1", "0"):
+            monkeypatch.setenv("MWF_B200_TILE_PREDICT", predict)
+            with mw.Batch(o, [(t, q)]) as b:
+                b.upload()
+                b.run()
+                assert b.fetch() == [want], (name, predict)
+                launches[name, predict] = b.launches
+    assert launches["far", "1"] < launches["far", "0"]      # the failed attempt is gone
+    assert launches["near", "1"] == launches["near", "0"]   # s^2 fits: nothing changes
+
+
 def test_reference_cli_linked_against_this_library(tmp_path):
     """the reference's own, unmodified main.c, compiled against include/miniwfa.h and linked with
     libminiwfa_b200.so in place of miniwfa.o kalloc.o mwf-dbg.o (oracle/_ref/test-mwf-dropin, built where /root/reference
