@@ -436,6 +436,44 @@ def test_segmented_traceback(monkeypatch):
         assert mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR), t, q) == w
 
 
+def test_concurrent_host_threads():
+    """The library keeps no alignment state between calls (stateless, one km per thread): several host threads calling
+    the entry points at once -- batches on the tile engine and on the streaming kernel, mwf_wfa_chain with the device front end,
+    single pairs with CIGAR -- get the results of the same calls made one after the other."""
+    import threading
+    mw.set_kernel(mw.KERNEL_AUTO)
+    jobs = []
+    for i in range(8):
+        if i % 4 == 0:
+            pairs = synth.make_batch(6, 12000, 0.04, 100 + i)
+            jobs.append((lambda pairs=pairs: mw.wfa_exact_batch(mw.opt_init(), pairs)))
+        elif i % 4 == 1:
+            pairs = synth.make_batch(300, 200, 0.05, 200 + i)
+            jobs.append((lambda pairs=pairs: mw.wfa_exact_batch(mw.opt_init(flag=mw.F_CIGAR), pairs)))
+        elif i % 4 == 2:
+            t, q = synth.make_pair(60000, 0.03, 300 + i)
+            jobs.append((lambda t=t, q=q: mw.wfa_chain(mw.opt_init(flag=mw.F_CIGAR, step=5000), t, q)))
+        else:
+            t, q = synth.make_pair(15000, 0.05, 400 + i)
+            jobs.append((lambda t=t, q=q: mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR, step=700), t, q)))
+    want = [j() for j in jobs]
+    for _ in range(3):
+        got = [None] * len(jobs)
+        errs = []
+
+        def work(k):
+            try:
+                got[k] = jobs[k]()
+            except Exception as e:  # pragma: no cover
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        assert not errs and got == want
+
+
 def test_arena_overflow_predicted_from_shared_kmers(monkeypatch):
     """A few very long pairs whose s^2 traceback bytes cannot fit skip the all-at-once attempt: the shared 13-mer fraction
     (mwf_b200_kmer_shared) gives a low estimate of s beforehand.  Forced here on a 12 kb pair with a 300 kB arena: the launch
