@@ -273,7 +273,7 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
     b_launches = int(b.launches)
-    launches = b_launches * args.steps
+    launches = int(sum_over_ranks(float(b_launches * args.steps)))  # kernels launched inside the timed region, all ranks
     res = b.fetch()
     fam_names = {mw.KERNEL_CTA: "cta", mw.KERNEL_GRID: "grid", mw.KERNEL_TILE: "tile"}
     kernel_used = fam_names.get(b.kernel_used, "?")
