@@ -1077,8 +1077,9 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		max_sbound = std::max(max_sbound, sb);
 		b->order[i] = i;
 	}
-	std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
-		return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
+	if (max_len >= 1024) /* longest first, for balance; pairs this short take microseconds each and sorting 1e5 of them costs more than it saves */
+		std::stable_sort(b->order.begin(), b->order.end(), [&](int a, int c) {
+			return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
 	b->seq_bytes = off + 64, b->cigar_words = cw;
 	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
 	b->max_len = max_len, b->max_sbound = max_sbound, b->arena_full = 0, b->d_nseg = 0, b->d_seqp = 0, b->d_packed = 0;
