@@ -33,6 +33,7 @@
 #define MWF_B200_H
 
 #include <stdint.h>
+#include <stddef.h>
 #include "miniwfa.h"
 
 #ifdef __cplusplus
@@ -96,6 +97,9 @@ void    mwf_b200_kmer_free(uint64_t *hits);
 /* The counting part of mwf_ksim (miniwfa.c:786-812): k-mers in s1, k-mers in s2, sum over distinct k-mers of
  * min(copies in s1, copies in s2).  The caller does the two divisions. */
 void    mwf_b200_kmer_shared(int32_t l1, const char *s1, int32_t l2, const char *s2, int32_t k, int64_t *n1, int64_t *n2, int64_t *shared);
+/* host scratch from the library's cache of pinned buffers (resident memory: no page faults on reuse); NULL is never returned */
+void   *mwf_b200_host_scratch(size_t bytes);
+void    mwf_b200_host_scratch_free(void *p);
 int64_t mwf_b200_kmer_launches(void); /* kernels launched by the two calls above since the library was loaded */
 
 #ifdef __cplusplus

@@ -251,6 +251,17 @@ extern "C" int64_t mwf_b200_kmer_hits(int32_t tl, const char *ts, int32_t ql, co
 
 extern "C" void mwf_b200_kmer_free(uint64_t *hits) { ws_free(hits); }
 
+extern "C" void *mwf_b200_host_scratch(size_t bytes)
+{
+	void *p = 0;
+	if (mwf_b200_device_count() <= 0) die("no CUDA device: this library has no CPU fallback");
+	CUDA_OK(cudaSetDevice(mwf_b200_get_device()));
+	ws_alloc(&p, bytes, true, 0);
+	return p;
+}
+
+extern "C" void mwf_b200_host_scratch_free(void *p) { ws_free(p); }
+
 extern "C" void mwf_b200_kmer_shared(int32_t l1, const char *s1, int32_t l2, const char *s2, int32_t k, int64_t *n1, int64_t *n2, int64_t *shared)
 {
 	KmerList L;

@@ -120,29 +120,52 @@ static void sort64(void *km, uint64_t *a, size_t n)
  * a dozen cache misses -- those go through samp[b] = tailv[64 b], which stays in cache, and then one 64-entry block.
  * Same lo as plain bisection, so the same chain as the reference's mg_lis_64. */
 #define LIS_BLK 64
-#define LIS_AHEAD 16
+#define LIS_AHEAD 16 /* a power of two */
+#define LIS_WS_MIN 65536
+
+/* the largest index in [lo, hi) whose value is below x, where a[lo] counts as below x whatever it holds (lo may be the unused
+ * slot 0); a[] increasing on (lo, hi).  Branch-free bisection: the outcome of each comparison is data, not control. */
+static inline int32_t lis_last_below(const uint64_t *a, int32_t lo, int32_t hi, uint64_t x)
+{
+	int32_t n = hi - lo;
+	while (n > 1) {
+		const int32_t half = n >> 1;
+		lo = a[lo + half] < x ? lo + half : lo;
+		n -= half;
+	}
+	return lo;
+}
 
 static uint64_t *longest_increasing(void *km, int32_t n, const uint64_t *v, int32_t *n_out)
 {
-	int32_t *tail, *prev, i, len = 0, at;
+	int32_t *tail, *prev, i, len = 0, at, guess[LIS_AHEAD];
 	uint64_t *tailv, *samp, *out;
+	const size_t n_samp = (size_t)n / LIS_BLK + 2;
+	/* Large inputs take the ~16 bytes per match of scratch from the library's cache of pinned host buffers: memory that is
+	 * already resident, where a fresh kmalloc of tens of MB is paid for in page faults on every call. */
+	void *ws = n >= LIS_WS_MIN ? mwf_b200_host_scratch(sizeof(uint64_t) * ((size_t)n + 1 + n_samp) + sizeof(int32_t) * (2 * (size_t)n + 2)) : 0;
 	*n_out = 0;
 	if (n <= 0) return 0;
-	tail = (int32_t*)kmalloc(km, sizeof(int32_t) * ((size_t)n + 1));
-	tailv = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)n + 1));
-	samp = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)n / LIS_BLK + 2));
-	prev = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)n);
+	if (ws) {
+		tailv = (uint64_t*)ws, samp = tailv + n + 1;
+		tail = (int32_t*)(samp + n_samp), prev = tail + n + 1;
+	} else {
+		tail = (int32_t*)kmalloc(km, sizeof(int32_t) * ((size_t)n + 1));
+		tailv = (uint64_t*)kmalloc(km, sizeof(uint64_t) * ((size_t)n + 1));
+		samp = (uint64_t*)kmalloc(km, sizeof(uint64_t) * n_samp);
+		prev = (int32_t*)kmalloc(km, sizeof(int32_t) * (size_t)n);
+	}
+	for (i = 0; i < LIS_AHEAD; ++i) guess[i] = -1;
 	for (i = 0; i < n; ++i) {
 		const uint64_t x = v[i];
+		const int32_t g = guess[i & (LIS_AHEAD - 1)];
 		int32_t lo = len;
-		if (i + LIS_AHEAD < n && len >= 4 * LIS_BLK) { /* a stray match a few elements ahead: fetch the block it will land in */
+		guess[i & (LIS_AHEAD - 1)] = -1;
+		if (i + LIS_AHEAD < n && len >= 4 * LIS_BLK) { /* a stray match a few elements ahead: find and fetch the block it will land in */
 			const uint64_t y = v[i + LIS_AHEAD];
 			if (tailv[len - LIS_BLK] >= y) {
-				int32_t bl = 0, bh = len / LIS_BLK + 1;
-				while (bh - bl > 1) {
-					const int32_t bm = bl + ((bh - bl) >> 1);
-					if (samp[bm] < y) bl = bm; else bh = bm;
-				}
+				const int32_t bl = lis_last_below(samp, 0, len / LIS_BLK + 1, y);
+				guess[i & (LIS_AHEAD - 1)] = bl; /* (i + LIS_AHEAD) & (LIS_AHEAD - 1) is the same slot */
 				__builtin_prefetch(&tailv[bl * LIS_BLK + LIS_BLK / 4]), __builtin_prefetch(&tailv[bl * LIS_BLK + 3 * LIS_BLK / 4]);
 				__builtin_prefetch(&tail[bl * LIS_BLK + LIS_BLK / 4]), __builtin_prefetch(&tail[bl * LIS_BLK + 3 * LIS_BLK / 4]);
 			}
@@ -151,21 +174,17 @@ static uint64_t *longest_increasing(void *km, int32_t n, const uint64_t *v, int3
 			int32_t hi = len, step = 1; /* invariant: tailv[hi] >= x */
 			lo = hi - 1;
 			while (lo > 0 && tailv[lo] >= x && step < LIS_BLK) hi = lo, step <<= 1, lo = hi - step;
-			if (lo > 0 && tailv[lo] >= x) { /* far below the top */
-				int32_t bl = 0, bh = lo / LIS_BLK + 1; /* samp[bl] < x (or bl == 0), samp[bh] >= x (or bh past the last block) */
+			if (lo > 0 && tailv[lo] >= x) { /* far below the top: the block first (samp[b] = tailv[LIS_BLK b], b = 1 .. lo / LIS_BLK) */
+				const int32_t nb = lo / LIS_BLK;
+				int32_t bl;
 				hi = lo;
-				while (bh - bl > 1) {
-					const int32_t bm = bl + ((bh - bl) >> 1);
-					if (samp[bm] < x) bl = bm; else bh = bm;
-				}
+				if (g >= 0 && g <= nb && (g == 0 || samp[g] < x) && (g == nb || samp[g + 1] >= x)) bl = g; /* found while prefetching, still right */
+				else bl = lis_last_below(samp, 0, nb + 1, x);
 				lo = bl * LIS_BLK;
-				if (lo + LIS_BLK < hi) hi = lo + LIS_BLK; /* = LIS_BLK * bh, and samp[bh] >= x */
+				if (lo + LIS_BLK < hi) hi = lo + LIS_BLK; /* = LIS_BLK (bl + 1), and samp[bl + 1] >= x */
 			}
 			if (lo < 0) lo = 0;
-			while (hi - lo > 1) {
-				const int32_t mid = lo + ((hi - lo) >> 1);
-				if (tailv[mid] < x) lo = mid; else hi = mid;
-			}
+			lo = lis_last_below(tailv, lo, hi, x);
 		}
 		prev[i] = lo > 0 ? tail[lo] : -1;
 		tail[lo + 1] = i, tailv[lo + 1] = x;
@@ -174,10 +193,8 @@ static uint64_t *longest_increasing(void *km, int32_t n, const uint64_t *v, int3
 	}
 	out = (uint64_t*)kmalloc(km, sizeof(uint64_t) * (size_t)len);
 	for (i = len - 1, at = tail[len]; i >= 0; --i) out[i] = v[at], at = prev[at];
-	kfree(km, prev);
-	kfree(km, samp);
-	kfree(km, tailv);
-	kfree(km, tail);
+	if (ws) mwf_b200_host_scratch_free(ws);
+	else kfree(km, prev), kfree(km, samp), kfree(km, tailv), kfree(km, tail);
 	*n_out = len;
 	return out;
 }

@@ -34,6 +34,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 #include <algorithm>
 #include <vector>
 #include <atomic>
@@ -1679,11 +1680,26 @@ extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pa
                                     const int32_t *tl, const char *const *ts,
                                     const int32_t *ql, const char *const *qs, mwf_rst_t *r)
 {
+	const bool timing = getenv("MWF_B200_BATCH_TIMING") != 0; /* phase times to stderr */
+	double t[6] = { 0, 0, 0, 0, 0, 0 };
+	struct timespec ts0;
+#define BATCH_T(i_) do { if (timing) { clock_gettime(CLOCK_MONOTONIC, &ts0); t[i_] = 1e3 * ts0.tv_sec + 1e-6 * ts0.tv_nsec; } } while (0)
+	BATCH_T(0);
 	mwf_b200_batch_t *b = mwf_b200_batch_create(opt, n_pairs, tl, ql);
+	BATCH_T(1);
 	mwf_b200_batch_upload(b, ts, qs);
+	BATCH_T(2);
 	mwf_b200_batch_run(b);
+	mwf_b200_batch_wait(b);
+	BATCH_T(3);
 	mwf_b200_batch_fetch(b, km, r);
+	BATCH_T(4);
 	mwf_b200_batch_destroy(b);
+	BATCH_T(5);
+#undef BATCH_T
+	if (timing)
+		fprintf(stderr, "[mwf_b200] batch of %d: create %.2f, upload %.2f, run %.2f, fetch %.2f, destroy %.2f ms\n", n_pairs,
+		        t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
 }
 
 #include "kmer_front.cuh"

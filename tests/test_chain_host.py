@@ -37,6 +37,8 @@ void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n, const int32_
 }
 int64_t mwf_b200_kmer_hits(int32_t tl, const char *ts, int32_t ql, const char *qs, int32_t k, int32_t max_occ, uint64_t **hits) { abort(); }
 void mwf_b200_kmer_free(uint64_t *hits) { abort(); }
+void *mwf_b200_host_scratch(size_t bytes) { return malloc(bytes); }
+void mwf_b200_host_scratch_free(void *p) { free(p); }
 void mwf_b200_kmer_shared(int32_t l1, const char *s1, int32_t l2, const char *s2, int32_t k, int64_t *n1, int64_t *n2, int64_t *shared) { abort(); }
 """
 
