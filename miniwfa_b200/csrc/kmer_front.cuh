@@ -152,7 +152,6 @@ struct KmerList {
 	cudaStream_t st;
 	unsigned char *d_seq;
 	unsigned long long *d_keys[2], *d_cnt, *h_cnt; /* cnt: [0] target k-mers, [1] query k-mers, [2] group result */
-	void *d_tmp;
 	unsigned long long *sorted;
 	long long n_all, n_valid;
 	int launches;
