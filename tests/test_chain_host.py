@@ -35,6 +35,8 @@ void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n, const int32_
 		orc_free(o.cigar);
 	}
 }
+""" + r"""
+/* the device entry points mwf_chain.c can call: never reached with MWF_B200_CHAIN_FRONT=host; host scratch is plain malloc here */
 int64_t mwf_b200_kmer_hits(int32_t tl, const char *ts, int32_t ql, const char *qs, int32_t k, int32_t max_occ, uint64_t **hits) { abort(); }
 void mwf_b200_kmer_free(uint64_t *hits) { abort(); }
 void *mwf_b200_host_scratch(size_t bytes) { return malloc(bytes); }
@@ -101,3 +103,86 @@ def test_host_chain_large_pair_against_reference(host_chain, monkeypatch):
         ref.mwf_wfa_chain(None, ctypes.byref(o), len(t), t, len(q), q, ctypes.byref(rr))
         assert got[:2] == (rr.s, rr.n_cigar)
         assert got[2] == (rr.cigar[:rr.n_cigar] if rr.n_cigar > 0 else [])
+
+
+LIS_WRAP = r"""
+#include <stdlib.h>
+#include "@CSRC@/mwf_chain.c"
+/* test hook: the static longest_increasing() of mwf_chain.c */
+int32_t lis_values(int32_t n, const uint64_t *v, uint64_t *out)
+{
+	int32_t m = 0, i;
+	uint64_t *a = longest_increasing(0, n, v, &m);
+	for (i = 0; i < m; ++i) out[i] = a[i];
+	kfree(0, a);
+	return m;
+}
+void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n, const int32_t *tl, const char *const *ts,
+                         const int32_t *ql, const char *const *qs, mwf_rst_t *r) { abort(); }
+int64_t mwf_b200_kmer_hits(int32_t tl, const char *ts, int32_t ql, const char *qs, int32_t k, int32_t max_occ, uint64_t **hits) { abort(); }
+void mwf_b200_kmer_free(uint64_t *hits) { abort(); }
+void *mwf_b200_host_scratch(size_t bytes) { return malloc(bytes); }
+void mwf_b200_host_scratch_free(void *p) { free(p); }
+void mwf_b200_kmer_shared(int32_t l1, const char *s1, int32_t l2, const char *s2, int32_t k, int64_t *n1, int64_t *n2, int64_t *shared) { abort(); }
+"""
+
+
+def _py_lis(v):
+    """mg_lis_64 (miniwfa.c:678-697) restated: patience piles by bisection, predecessor = tail of the pile below."""
+    import bisect
+    tails, tail_idx, prev = [], [], []
+    for i, x in enumerate(v):
+        lo = bisect.bisect_left(tails, x)  # number of piles whose tail is below x (values are distinct)
+        prev.append(tail_idx[lo - 1] if lo > 0 else -1)
+        if lo == len(tails):
+            tails.append(x)
+            tail_idx.append(i)
+        else:
+            tails[lo] = x
+            tail_idx[lo] = i
+    out, at = [], tail_idx[-1] if tail_idx else -1
+    while at >= 0:
+        out.append(v[at])
+        at = prev[at]
+    return out[::-1]
+
+
+def test_longest_increasing_against_plain_patience(tmp_path):
+    """The galloping / sampled two-level / prefetch-guess search of longest_increasing() picks exactly the elements plain
+    bisection picks: random permutations, near-sorted chains with 1..30 % strays (the k-mer match pattern), descending runs,
+    sizes on both sides of the pinned-scratch threshold."""
+    import random
+    src = tmp_path / "lis_wrap.c"
+    src.write_text(LIS_WRAP.replace("@CSRC@", os.path.join(ROOT, "miniwfa_b200", "csrc")))
+    so = str(tmp_path / "liblis.so")
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), str(src),
+                    os.path.join(ROOT, "miniwfa_b200", "csrc", "kalloc.c"), "-o", so], check=True)
+    L = ctypes.CDLL(so)
+    L.lis_values.argtypes = [ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    L.lis_values.restype = ctypes.c_int32
+    rng = random.Random(17)
+
+    def check(v):
+        n = len(v)
+        a = (ctypes.c_uint64 * max(1, n))(*v)
+        out = (ctypes.c_uint64 * max(1, n))()
+        m = L.lis_values(n, a, out)
+        assert out[:m] == _py_lis(v), n
+
+    check([])
+    check([5])
+    for n in (2, 3, 63, 64, 65, 127, 128, 129, 1000, 5000):
+        for _ in range(6):
+            check(rng.sample(range(10 * n), n))
+        check(list(range(n, 0, -1)))
+        check(list(range(1, n + 1)))
+    for n, stray in ((20000, 0.01), (20000, 0.1), (20000, 0.3), (70000, 0.1), (150000, 0.1), (150000, 0.02)):
+        # matches sorted by target: mostly query = target + drift (a chain), some strays anywhere, as query << 32 | target
+        v, drift = [], 0
+        for t in range(n):
+            if rng.random() < 0.01:
+                drift += rng.randint(-3, 3)
+            q = rng.randrange(2 * n) if rng.random() < stray else max(0, t + 1000 + drift)
+            v.append(q << 32 | t)
+        check(v)
+
