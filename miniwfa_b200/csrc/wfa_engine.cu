@@ -67,6 +67,7 @@ struct PairOut {
 	long long n_iter;
 	long long cigar_pos;    /* word offset of the first CIGAR word */
 	int status, pad_;
+	int end_s, end_i, end_k, pad2_; /* where wf_traceback's walk stopped: what MWF_F_DEBUG prints (miniwfa.c:367) */
 };
 
 struct KParams {
@@ -601,7 +602,7 @@ __device__ bool trace_checkpoints(const Job &J, const Pen &pen, int n_snap, int 
  * of the two insertion and the two deletion states.  Lanes 0..8 fetch all nine as soon as the current cell is known, so the
  * row-table lookup and the byte are in flight during the match run of the cell instead of after it, and the match runs' sequence
  * lines are prefetched 256 bases ahead (150 kb pair, 10 924 CIGAR operations: 7.5 -> 6.8 ms). */
-__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end)
+__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state)
 {
 	const int lane = threadIdx.x & 31, doff = J.doff;
 	int i = J.ql - 1, k = J.tl - 1, row = s_final, n_out = 0, cur_op = -1;
@@ -657,6 +658,7 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 		xs = xs_next;
 	}
 #undef SUCCESSORS
+	end_state[0] = row, end_state[1] = i, end_state[2] = k; /* :367 */
 	if (i >= 0) CIG_PUSH(1, (uint32_t)(i + 1));       /* :368 */
 	else if (k >= 0) CIG_PUSH(2, (uint32_t)(k + 1));  /* :369 */
 	if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; }
@@ -688,7 +690,7 @@ __device__ void run_pair(G &g, const KParams &P, int pi, int slot, int *smem)
 	J.slo = smem + 8, J.shi = smem + 8 + n;
 
 	PassOut po;
-	int st, n_cigar = 0, n_seg = 0;
+	int st, n_cigar = 0, n_seg = 0, end_state[3] = { 0, 0, 0 };
 	if (!P.is_tb) {
 		st = run_pass<MODE_SCORE>(g, P, J, 0, po);
 	} else {
@@ -705,7 +707,7 @@ __device__ void run_pair(G &g, const KParams &P, int pi, int slot, int *smem)
 		}
 		if (st == ST_OK) st = run_pass<MODE_TB>(g, P, J, n_seg, po);
 		if (st == ST_OK && g.leader_cta() && threadIdx.x < 32)
-			n_cigar = traceback_warp(J, P.pen, po.s, po.last, P.cigar + pd.cigar_off + pd.cigar_cap);
+			n_cigar = traceback_warp(J, P.pen, po.s, po.last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state);
 	}
 	if (g.rank() == 0) {
 		PairOut o;
@@ -714,6 +716,7 @@ __device__ void run_pair(G &g, const KParams &P, int pi, int slot, int *smem)
 		o.n_iter = po.n_iter;
 		o.cigar_pos = pd.cigar_off + pd.cigar_cap - n_cigar;
 		o.status = st, o.pad_ = 0;
+		o.end_s = end_state[0], o.end_i = end_state[1], o.end_k = end_state[2], o.pad2_ = 0;
 		P.outs[pi] = o;
 	}
 }
@@ -859,6 +862,18 @@ static bool ws_alloc(void **out, size_t bytes, bool host, int dev)
 	return true;
 }
 
+/* Per-device byte cap of the cache: $MWF_B200_CACHE_GB, default half of the device's memory.  After a batch that took nearly
+ * all of HBM for its traceback arena the library hands that buffer back to the driver instead of sitting on it, so that other
+ * allocators of the process (torch, NCCL, the caller's own) are not starved; mwf_b200_release_cache() frees the rest. */
+static size_t ws_cache_cap(void)
+{
+	const int gb = env_int("MWF_B200_CACHE_GB", -1);
+	if (gb >= 0) return (size_t)gb << 30;
+	size_t free_b = 0, total_b = 0;
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return (size_t)64 << 30; }
+	return total_b / 2;
+}
+
 static void ws_free(void *p)
 {
 	if (p == 0) return;
@@ -867,9 +882,26 @@ static void ws_free(void *p)
 		std::lock_guard<std::mutex> lk(g_ws_mu);
 		std::unordered_map<void*, WsEntry>::iterator it = g_ws_live.find(p);
 		if (it == g_ws_live.end()) return;
-		g_ws_free.push_back(it->second);
+		const WsEntry e = it->second;
 		g_ws_live.erase(it);
-		while (g_ws_free.size() > 48) { drop.push_back(g_ws_free.front()); g_ws_free.erase(g_ws_free.begin()); }
+		/* the cache is bounded in entries and, per device, in bytes (ws_cache_cap) */
+		static const size_t cap = ws_cache_cap();
+		if (!e.host && e.bytes > cap) drop.push_back(e);
+		else {
+			g_ws_free.push_back(e);
+			while (g_ws_free.size() > 48) { drop.push_back(g_ws_free.front()); g_ws_free.erase(g_ws_free.begin()); }
+			if (!e.host) {
+				size_t held = 0;
+				for (size_t i = 0; i < g_ws_free.size(); ++i)
+					if (!g_ws_free[i].host && g_ws_free[i].dev == e.dev) held += g_ws_free[i].bytes;
+				for (size_t i = 0; held > cap && i < g_ws_free.size(); ) { /* oldest first */
+					if (g_ws_free[i].host || g_ws_free[i].dev != e.dev) { ++i; continue; }
+					held -= g_ws_free[i].bytes;
+					drop.push_back(g_ws_free[i]);
+					g_ws_free.erase(g_ws_free.begin() + i);
+				}
+			}
+		}
 	}
 	for (size_t i = 0; i < drop.size(); ++i) ws_really_free(drop[i]);
 }
@@ -927,7 +959,7 @@ struct mwf_b200_batch {
 	cudaEvent_t ev0, ev1;
 	double kernel_ms;
 	int64_t launches, h2d, d2h;
-	bool ran;
+	bool ran, timed; /* timed: kernel_ms of the last run has been taken (mwf_b200_batch_wait may be called more than once) */
 	/* tile engine (wfa_tile.cuh) */
 	struct TileGeom { int CPT, NT, T, HL, W, grid; size_t smem; tile_kernel_fn fn, fn_score; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
 	int n_geom, tR, wave_pairs, s_limit;
@@ -1022,6 +1054,20 @@ static void free_tile(mwf_b200_batch_t *b)
 	ws_free(b->d_rowtab); ws_free(b->d_arena); ws_free(b->d_seg);
 	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_tmisc = 0, b->d_nseg = 0, b->d_rowtab = 0, b->d_arena = 0, b->d_seg = 0;
 	b->arena_total = 0, b->rowtab_stride = 0;
+}
+
+/* The dynamic shared-memory limit is an attribute of the kernel function, process-wide per device: it is raised to the device's
+ * opt-in maximum once and never lowered, so that batches with different penalties (different tile sizes) created concurrently
+ * on several host threads cannot shrink it under one another between cudaFuncSetAttribute and the launch. */
+static void tile_smem_optin(tile_kernel_fn fn, int dev, int smem_optin)
+{
+	static std::mutex mu;
+	static std::vector<std::pair<void*, int> > done;
+	std::lock_guard<std::mutex> lk(mu);
+	for (size_t i = 0; i < done.size(); ++i)
+		if (done[i].first == (void*)fn && done[i].second == dev) return;
+	CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+	done.push_back(std::make_pair((void*)fn, dev));
 }
 
 extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t n_pairs, const int32_t *tl, const int32_t *ql)
@@ -1207,14 +1253,14 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			int per_sm = 0;
 			G.fn = tile_kernel_for(b->is_tb, G.CPT);
 			G.fn_score = tile_kernel_for(false, G.CPT);
-			CUDA_OK(cudaFuncSetAttribute(G.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
-			CUDA_OK(cudaFuncSetAttribute(G.fn_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+			tile_smem_optin(G.fn, b->dev, smem_optin);
+			tile_smem_optin(G.fn_score, b->dev, smem_optin);
 			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, G.fn, G.NT, G.smem));
 			if (per_sm < 1) die("tile kernel does not fit on an SM");
 			G.grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
 		}
 	} else alloc_streaming(b);
-	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false;
+	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false, b->timed = false;
 	return b;
 }
 
@@ -1554,17 +1600,18 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 	}
 	CUDA_OK(cudaEventRecord(b->ev1, b->stream));
 	CUDA_OK(cudaMemcpyAsync(b->h_outs, b->d_outs, sizeof(PairOut) * b->n, cudaMemcpyDeviceToHost, b->stream));
-	b->ran = true;
+	b->ran = true, b->timed = false;
 }
 
 extern "C" void mwf_b200_batch_wait(mwf_b200_batch_t *b)
 {
 	CUDA_OK(cudaSetDevice(b->dev));
 	CUDA_OK(cudaStreamSynchronize(b->stream));
-	if (!b->ran) return;
+	if (!b->ran || b->timed) return;
 	float ms = 0;
 	CUDA_OK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
 	b->kernel_ms = ms;
+	b->timed = true;
 	/* pairs whose slot ran out of arena are retried one at a time with the whole arena */
 	std::vector<int> retry;
 	for (int i = 0; i < b->n; ++i) {
@@ -1619,6 +1666,8 @@ extern "C" void mwf_b200_batch_fetch(mwf_b200_batch_t *b, void *km, mwf_rst_t *r
 	for (int i = 0; i < b->n; ++i) {
 		const PairOut &o = b->h_outs[i];
 		r[i].s = o.s, r[i].n_iter = o.n_iter, r[i].n_cigar = 0, r[i].cigar = 0;
+		if ((b->opt.flag & MWF_F_DEBUG) && b->is_tb && o.s >= 0) /* wf_traceback's line, miniwfa.c:367: it counts traceback rows, row = score - 1 */
+			fprintf(stderr, "s0=%d, s=%d, i=%d, k=%d\n", o.s - 1, o.end_s - 1, o.end_i, o.end_k);
 		if (o.s >= 0 && o.n_cigar > 0) {
 			r[i].n_cigar = o.n_cigar;
 			r[i].cigar = (uint32_t*)kmalloc(km, sizeof(uint32_t) * (size_t)o.n_cigar);

@@ -174,6 +174,7 @@ __global__ void wfa_tile_init_kernel(const TParams P)
 		if (c->status == TS_DONE) {
 			PairOut o;
 			o.s = 0, o.n_cigar = 0, o.n_iter = 0, o.cigar_pos = pd.cigar_off + pd.cigar_cap, o.status = ST_OK, o.pad_ = 0;
+			o.end_s = 0, o.end_i = -1, o.end_k = -1, o.pad2_ = 0;
 			P.outs[pi] = o;
 		} else atomicAdd(P.n_running, 1);
 	}
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			o.n_cigar = 0, o.n_iter = c->n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap;
 			o.status = status == TS_DONE ? ST_OK : status == TS_STOPPED ? ST_STOPPED : status == TS_ARENA ? ST_ARENA : ST_SHRINK;
 			o.pad_ = 0;
+			o.end_s = 0, o.end_i = 0, o.end_k = 0, o.pad2_ = 0;
 			P.outs[pi] = o;
 		}
 	}
@@ -872,8 +874,10 @@ __global__ void wfa_tile_traceback_kernel(const TParams P)
 	J.T8 = P.seq + pd.t_off, J.Q8 = P.seq + pd.q_off;
 	J.arena = P.arena, J.arena_cap = P.arena_cap;
 	J.rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
-	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap);
+	int end_state[3];
+	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state);
 	if (threadIdx.x == 0) {
+		P.outs[pi].end_s = end_state[0], P.outs[pi].end_i = end_state[1], P.outs[pi].end_k = end_state[2];
 		P.outs[pi].n_cigar = n_cigar;
 		P.outs[pi].cigar_pos = pd.cigar_off + pd.cigar_cap - n_cigar;
 	}
@@ -981,12 +985,14 @@ __global__ void wfa_tile_trace_seg_kernel(const TParams P, int j)
 		last = (state > 0 && ext) ? state : 0;
 	}
 	if (j == 0 || i < 0 || k < 0) { /* the walk is over: leading gap (:368-369), flush, result record */
+		const int end_i = i, end_k = k;
 		if (i >= 0) CIG_PUSH(1, (uint32_t)(i + 1));
 		else if (k >= 0) CIG_PUSH(2, (uint32_t)(k + 1));
 		if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; }
 		if (lane == 0) {
 			PairOut o;
 			o.s = t.s_final, o.n_cigar = n_out, o.n_iter = t.n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap - n_out, o.status = ST_OK, o.pad_ = 0;
+			o.end_s = row, o.end_i = end_i, o.end_k = end_k, o.pad2_ = 0;
 			P.outs[pi] = o;
 			tsp->fwd_status = TS_IDLE; /* nothing left to do in the remaining segments */
 		}
