@@ -104,6 +104,11 @@ def set_kernel(kernel):
     lib().mwf_b200_set_kernel(int(kernel))
 
 
+def release_cache():
+    """mwf_b200_release_cache(): free every cached device / pinned-host workspace."""
+    lib().mwf_b200_release_cache()
+
+
 def _take(r, km=None):
     """Copy a result out of an mwf_rst_t and release its CIGAR (allocated from km / malloc)."""
     cig = [r.cigar[i] for i in range(r.n_cigar)] if r.n_cigar > 0 else []

@@ -1107,7 +1107,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 
 	/* layout of sequences, CIGAR buffers, work order */
 	long long max_len = 0, max_sbound = 0;
-	size_t off = 0, cw = 0;
+	size_t off = 256, cw = 0; /* (front slack: the probe of a cell off the matrix reads position d < 0 of its query, never used) */
 	b->pairs.resize(n_pairs);
 	b->order.resize(n_pairs);
 	for (int i = 0; i < n_pairs; ++i) {
@@ -1153,7 +1153,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		G.HL = G.T;
 		G.NT = env_int("MWF_B200_TILE_THREADS", lat ? 512 : 128);
 		G.W = G.CPT * G.NT;
-		G.smem = (size_t)b->tR * G.W * 4 + 64;
+		G.smem = (size_t)b->tR * G.W * 4 + 64 + sizeof(StepTab) * (size_t)std::max(G.T, 2);
 		G.fn = 0, G.fn_score = 0, G.grid = 0;
 		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)smem_optin &&
 			(G.W - 2 * G.HL) / 2 - 4 >= 2 * G.HL + n + 8;
@@ -1386,6 +1386,8 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
+	/* (the fast path addresses the sequences by 32-bit bit positions inside the sequence buffer) */
+	P.fast = env_int("MWF_B200_TILE_FAST", 1) && b->pen.e1 <= 2 && b->pen.e2 <= 2 && (long long)b->seq_bytes < (1LL << 28);
 	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
 		const mwf_b200_batch::TileGeom &G = b->geom[g < b->n_geom ? g : 0];

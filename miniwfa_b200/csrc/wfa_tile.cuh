@@ -86,6 +86,7 @@ struct TParams {
 	int *n_seg;                /* [n_pairs] */
 	int seg_stride, seg_use, step; /* seg_use: this pass collapses the band at the checkpoints (pass 2, miniwfa.c:413-416) */
 	int s_limit;               /* no alignment of the batch can cost more (all-gap bound): a guard against endless runs */
+	int fast;                  /* interior tiles of the 4-cells-per-thread geometry keep the gap rows in registers (tile_cells_fast) */
 	/* segmented traceback */
 	int snap_P, snapdir_stride, snap_take; /* snap_take: save a snapshot whenever s is a multiple of snap_P (a multiple of 256) */
 	int32_t *snap_arena;
@@ -613,6 +614,139 @@ __device__ __forceinline__ void tile_cells_overlap(uint32_t sb, const int4 &qh, 
 	o.tb = tbw;
 }
 
+/*
+ * The interior step with the gap rows in registers ("fast" path: 4 cells per thread, e1 <= 2 and e2 <= 2).
+ *
+ * E1/F1 of score s-e1 and E2/F2 of score s-e2 at a thread's own diagonals are what the same thread computed e1 / e2 steps
+ * earlier, so they stay in registers (two sets when the depth is 2; the step loop is unrolled by two and alternates them).
+ * Shared memory keeps the H ring, plus of the gap rows only what another warp reads -- the last cell of lane 31 (E rows) and the
+ * first cell of lane 0 (F rows) -- until the last e1 / e2 steps of the block, whose gap rows are stored whole for the bulk copy
+ * back to the state buffer.  Per step a thread issues 3 row loads and 1 row store instead of 5-7 and 5, and the row offsets of
+ * the step come from a small per-block table in shared memory (3 broadcast loads) instead of indexed kernel-parameter reads.
+ * The integer ALU pipe is what bounds this kernel (two cycles per warp instruction): the probe positions are kept pre-multiplied
+ * by the code width, so that one shift gives the word index and the funnel shift takes its amount as it is; the first differing
+ * code is popc(~x & (x - 1)), which needs no test for x == 0.
+ * Same arithmetic as tile_cells<MODE, false, 4> (wf_next_score / wf_next_tb, miniwfa.c:261-308; first probe of
+ * wf_extend1_padded, :212-226).
+ */
+struct StepTab { int4 h, e; }; /* {Hx, Ho1, Ho2, nH}, {pE1, pE2, nE1, nE2}: byte offsets of the rows of one step; an F row lies a fixed distance after its E row */
+
+struct FastCtx {
+	uint32_t sb;              /* shared address of this thread's 4 cells in row 0 */
+	uint32_t nb, nb1, nb2;    /* lanes 0 / 31: the neighbour cell in an H row, in an E1 (lane 0) or F1 (lane 31) row, in an E2 or F2 row */
+	uint32_t bs1, bs2;        /* lanes 0 / 31: where this thread's outer gap cell goes -- lane 31: E row, cell 3; lane 0: F row, cell 0 */
+	uint32_t f1off, f2off;    /* byte distance from an E1 row to the F1 row of the same score, E2 to F2 */
+	bool left, right, edge_lane, bnd_lane; /* lane 0; lane 31; the neighbour cell exists; lane 0 or 31 */
+	const uint32_t *seqw;     /* the words both sequences are probed in (packed codes, or the raw bytes) */
+	uint32_t tbits, dq0;      /* bit offset of the target in seqw; (bit offset of the query) - tbits + d0 x code width */
+	uint32_t cb, cb2, cb3;    /* code width in bits: 2, 4 or 8; twice, three times that */
+	int lcb;                  /* log2(cb) */
+	int d0, tl, ql, tlm1, qlm1d0; /* tl - 1; ql - 1 - d0 */
+};
+
+/* number of trailing zero bits; 0xffffffff for 0.  BREV + FLO run on the XU pipe, not on the integer ALU pipe that bounds this
+ * kernel (written in C, the compiler turns every form of this into popc(~x & (x - 1)) plus a test for zero: four ALU instructions) */
+__device__ __forceinline__ uint32_t ctz32_sat(uint32_t x)
+{
+	uint32_t r;
+	asm("{ .reg .b32 t; brev.b32 t, %1; bfind.shiftamt.u32 %0, t; }" : "=r"(r) : "r"(x));
+	return r;
+}
+
+template<int MODE>
+__device__ __forceinline__ void tile_cells_fast(const FastCtx &c, const StepTab *tab, const SeqView &sv,
+                                                int (&pe1)[4], int (&pf1)[4], int (&pe2)[4], int (&pf2)[4],
+                                                bool full1, bool full2, uint64_t *stepbar, bool wait, uint32_t parity,
+                                                int (&Hn)[4], uint32_t &tb_out)
+{
+	const int4 qh = tab->h, qe = tab->e;
+	int ho1[4], ho2[4], hx[4];
+	ldsv<4>(c.sb + qh.y, ho1); ldsv<4>(c.sb + qh.z, ho2); ldsv<4>(c.sb + qh.x, hx);
+	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		A1[j + 1] = max(ho1[j], pe1[j]), A2[j + 1] = max(ho2[j], pe2[j]);
+		C1[j + 1] = max(ho1[j], pf1[j]), C2[j + 1] = max(ho2[j], pf2[j]);
+		if (MODE != MODE_SCORE) bA1[j + 1] = ho1[j] < pe1[j], bA2[j + 1] = ho2[j] < pe2[j], bC1[j + 1] = ho1[j] < pf1[j], bC2[j + 1] = ho2[j] < pf2[j];
+	}
+	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
+	A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
+	C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+	C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	if (MODE != MODE_SCORE) {
+		const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
+		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+	}
+	int h0[4];
+	uint32_t tz[4];
+	bool ext[4];
+	uint32_t tbw = 0;
+	/* wf_next (:261-308) for cell j, then the first probe of its match run (:212-226): valid (:402) iff 0 <= k+1 <= tl and
+	 * 0 <= d+k+1 <= ql; a cell off the matrix probes position 0 of T and d of Q, which is readable and never used */
+#define FAST_CELL(j) do { \
+		const int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2] + 1, F2 = C2[j + 2] + 1; \
+		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = hx[j] + 1; \
+		const int H = max(hxp, gmx); \
+		if (MODE != MODE_SCORE) { \
+			const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4)); \
+			tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j); \
+		} \
+		pe1[j] = E1, pe2[j] = E2, pf1[j] = F1, pf2[j] = F2, h0[j] = H; \
+		const int tp = H + 1, qp = tp + c.d0 + j; \
+		ext[j] = (unsigned)tp <= (unsigned)c.tl && (unsigned)qp <= (unsigned)c.ql; \
+		const uint32_t tpb = (uint32_t)(ext[j] ? tp : 0) * c.cb + c.tbits; /* bit positions in seqw */ \
+		const uint32_t qpb = tpb + c.dq0 + (j == 0 ? 0u : j == 1 ? c.cb : j == 2 ? c.cb2 : c.cb3); \
+		const uint32_t *tw = c.seqw + (tpb >> 5), *qw = c.seqw + (qpb >> 5); \
+		tz[j] = ctz32_sat(__funnelshift_r(__ldg(tw), __ldg(tw + 1), tpb) ^ __funnelshift_r(__ldg(qw), __ldg(qw + 1), qpb)); \
+	} while (0)
+	FAST_CELL(1);
+	FAST_CELL(2);
+	if (wait) mbar_wait(stepbar, parity); /* every warp has finished the previous score */
+	{
+		const int o1 = lds1_if(c.nb + qh.y, c.edge_lane), o2 = lds1_if(c.nb + qh.z, c.edge_lane);
+		const int x1 = lds1_if(c.nb1 + qe.x, c.edge_lane), x2 = lds1_if(c.nb2 + qe.y, c.edge_lane);
+		const int m1 = max(o1, x1), m2 = max(o2, x2);
+		if (c.left) A1[0] = m1, A2[0] = m2;
+		if (c.right) C1[5] = m1, C2[5] = m2;
+		if (MODE != MODE_SCORE) {
+			if (c.left) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
+			if (c.right) bC1[5] = o1 < x1, bC2[5] = o2 < x2;
+		}
+	}
+	FAST_CELL(0);
+	FAST_CELL(3);
+#undef FAST_CELL
+	/* gap rows: whole in the last steps of the block (they go back to the state buffer), else only the cell another warp reads */
+	if (full1) { stsv<4>(c.sb + qe.z, pe1); stsv<4>(c.sb + qe.z + c.f1off, pf1); }
+	else {
+		const int v = c.right ? pe1[3] : pf1[0];
+		asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.b32 [%0], %1; }" :: "r"(c.bs1 + qe.z), "r"(v), "r"((int)c.bnd_lane) : "memory");
+	}
+	if (full2) { stsv<4>(c.sb + qe.w, pe2); stsv<4>(c.sb + qe.w + c.f2off, pf2); }
+	else {
+		const int v = c.right ? pe2[3] : pf2[0];
+		asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.shared.b32 [%0], %1; }" :: "r"(c.bs2 + qe.w), "r"(v), "r"((int)c.bnd_lane) : "memory");
+	}
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int k = min(h0[j] + (int)(tz[j] >> c.lcb), min(c.tlm1, c.qlm1d0 - j)); /* clamped to the matrix, as the reference's sentinels do */
+		Hn[j] = ext[j] ? k : h0[j];
+	}
+	if ((tz[0] | tz[1] | tz[2] | tz[3]) & 32) { /* rare: some probe matched in all positions (its tz is 0xffffffff, its k above is void) */
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int kmax = min(c.tlm1, c.qlm1d0 - j);
+			if (ext[j] && tz[j] == 0xffffffffu) {
+				const int k = min(h0[j] + (32 >> c.lcb), kmax);
+				Hn[j] = k < kmax ? tile_extend_more(sv, k, c.d0 + j, kmax) : k;
+			}
+		}
+	}
+	stsv<4>(c.sb + qh.w, Hn);
+	tb_out = tbw;
+}
+
 __device__ __forceinline__ bool on_matrix_u(int d, int k, int tl, int ql)
 {
 	return (unsigned)(k + 1) <= (unsigned)tl && (unsigned)(d + k + 1) <= (unsigned)ql;
@@ -631,11 +765,55 @@ __device__ __forceinline__ int alive_cells(int d0, int tl, int ql, const CellOut
 	return bits;
 }
 
+__device__ __forceinline__ int alive_cells4(int d0, int tl, int ql, const int (&H)[4], const int (&E1)[4], const int (&F1)[4], const int (&E2)[4], const int (&F2)[4])
+{
+	int bits = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int d = d0 + j;
+		if (on_matrix_u(d, H[j], tl, ql) || on_matrix_u(d, E1[j], tl, ql) || on_matrix_u(d, F1[j], tl, ql) ||
+		    on_matrix_u(d, E2[j], tl, ql) || on_matrix_u(d, F2[j], tl, ql)) bits |= 1 << j;
+	}
+	return bits;
+}
+
 template<int CPT> __device__ __forceinline__ void store_tb(uint8_t *p, uint32_t w) /* CPT traceback bytes, streaming store */
 {
 	if (CPT == 4) __stcs(reinterpret_cast<uint32_t*>(p), w);
 	else if (CPT == 2) __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)w);
 	else __stcs(reinterpret_cast<unsigned char*>(p), (unsigned char)w);
+}
+
+/* Tb steps of an interior tile on the fast path; E1 / E2 = the gap-extension penalties (1 or 2) = how many steps back the gap
+ * rows are read.  Returns the alive bits of this thread's cells (wf_stripe_shrink's input). */
+template<int MODE, int E1, int E2>
+__device__ __forceinline__ int tile_fast_block(const FastCtx &c, const StepTab *tab, const SeqView &sv, int d0, int Tb, int t_alive, int tl, int ql,
+                                               bool useful, uint8_t *tbp, long long tb_pitch, uint64_t *stepbar, uint32_t &step_phase)
+{
+	const int lane = threadIdx.x & 31;
+	int e1a[4], f1a[4], e1b[4], f1b[4], e2a[4], f2a[4], e2b[4], f2b[4], Hn[4];
+	int alive_bits = 0;
+	uint32_t tbw;
+	/* the gap rows the first steps read: scores s0-e+1 .. s0, out of the loaded state */
+	ldsv<4>(c.sb + tab[0].e.x, e1a); ldsv<4>(c.sb + tab[0].e.x + c.f1off, f1a);
+	ldsv<4>(c.sb + tab[0].e.y, e2a); ldsv<4>(c.sb + tab[0].e.y + c.f2off, f2a);
+	if (E1 == 2) { ldsv<4>(c.sb + tab[1].e.x, e1b); ldsv<4>(c.sb + tab[1].e.x + c.f1off, f1b); }
+	if (E2 == 2) { ldsv<4>(c.sb + tab[1].e.y, e2b); ldsv<4>(c.sb + tab[1].e.y + c.f2off, f2b); }
+#define FAST_STEP(X1, Y1, X2, Y2) do { \
+		tile_cells_fast<MODE>(c, tab + (t - 1), sv, X1, Y1, X2, Y2, t > Tb - E1, t > Tb - E2, stepbar, t > 1, step_phase & 1, Hn, tbw); \
+		if (t > 1) ++step_phase; \
+		if (MODE == MODE_TB) { if (useful) store_tb<4>(tbp, tbw); tbp += tb_pitch; } \
+		if (t > t_alive) alive_bits |= alive_cells4(d0, tl, ql, Hn, X1, Y1, X2, Y2); \
+		if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); } \
+	} while (0)
+	for (int t = 1;;) {
+		FAST_STEP(e1a, f1a, e2a, f2a);
+		if (++t > Tb) break;
+		FAST_STEP((E1 == 2 ? e1b : e1a), (E1 == 2 ? f1b : f1a), (E2 == 2 ? e2b : e2a), (E2 == 2 ? f2b : f2a));
+		if (++t > Tb) break;
+	}
+#undef FAST_STEP
+	return alive_bits;
 }
 
 /* threads per CTA and CTAs per SM the kernel is compiled for: 4 cells per thread keeps the instruction count per cell lowest
@@ -653,6 +831,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 	int32_t *rows = smem_tile;
 	int *sc = rows + (size_t)R * W;                          /* [0..2] flags, [3] item */
 	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8), *stepbar = reinterpret_cast<uint64_t*>(sc + 10);
+	StepTab *steptab = reinterpret_cast<StepTab*>(sc + 16); /* [max(T, 2)] row offsets of the steps of the block in flight */
 	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
 	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
 	const unsigned int n_items = P.cnt[it & 1].n_items;
@@ -688,6 +867,13 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
 		}
 		if (tid < 3) sc[tid] = 0;
+		if (CPT == 4 && P.fast && tid < max(Tb, 2)) { /* step tid+1 of the block works on score s0 + tid + 1 */
+			const int s = s0 + tid + 1;
+			const int4 h = P.tabH[s % n], a = P.tabE1[s % d1], b2 = P.tabE2[s % d2];
+			StepTab e;
+			e.h = h, e.e = make_int4(a.x, b2.x, a.z, b2.z);
+			steptab[tid] = e;
+		}
 		SeqView sv;
 		const int code_bits = P.packed ? P.packed[pi] : 0;
 		if (code_bits == 2) /* two-bit codes, 16 per word */
@@ -731,7 +917,29 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 		CellOut<CPT> o;
 		bool stepped = false;
 		if constexpr (CPT == 4) {
-			if (!special) { /* interior tile, throughput geometry: split-phase step barrier */
+			if (!special && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
+				FastCtx c;
+				const uint32_t rb = 4u * W;
+				c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
+				c.edge_lane = (lane == 0 && !no_left) || (lane == 31 && !no_right);
+				c.f1off = d1 * rb, c.f2off = d2 * rb; /* rows: H [n], E1 [d1], F1 [d1], E2 [d2], F2 [d2] */
+				c.nb = sb + (lane == 0 ? -4 : 16);
+				c.nb1 = c.nb + (lane == 0 ? 0u : c.f1off), c.nb2 = c.nb + (lane == 0 ? 0u : c.f2off);
+				c.bs1 = lane == 31 ? sb + 12 : sb + c.f1off, c.bs2 = lane == 31 ? sb + 12 : sb + c.f2off;
+				c.lcb = sv.s_amt, c.cb = 1u << sv.s_amt, c.cb2 = 2u << sv.s_amt, c.cb3 = 3u << sv.s_amt;
+				c.seqw = code_bits ? P.seqp : reinterpret_cast<const uint32_t*>(P.seq);
+				c.tbits = (uint32_t)(sv.T - c.seqw) << 5;
+				c.dq0 = ((uint32_t)(sv.Q - c.seqw) << 5) - c.tbits + ((uint32_t)d0 << sv.s_amt);
+				c.d0 = d0;
+				c.tl = tl, c.ql = ql, c.tlm1 = tl - 1, c.qlm1d0 = ql - 1 - d0;
+				const int e1 = P.pen.e1, e2 = P.pen.e2;
+				if (e1 == 2 && e2 == 1) alive_bits = tile_fast_block<MODE, 2, 1>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+				else if (e1 == 2) alive_bits = tile_fast_block<MODE, 2, 2>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+				else if (e2 == 1) alive_bits = tile_fast_block<MODE, 1, 1>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+				else alive_bits = tile_fast_block<MODE, 1, 2>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+				__syncthreads();
+				stepped = true;
+			} else if (!special) { /* interior tile, throughput geometry: split-phase step barrier */
 				for (int t = 1; t <= Tb; ++t) {
 					hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
 					const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];

@@ -20,6 +20,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_large():
+    """Full-size cases (BASELINE configs 2-5) from the unmodified reference: tests/golden/make_golden_large.py."""
+    with open(os.path.join(ROOT, "tests", "golden", "golden_large.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.fixture(scope="session")
 def product_lib():
     """The built product library (compiles it if needed; nvcc cross-compiles without a GPU)."""
     from miniwfa_b200 import build
