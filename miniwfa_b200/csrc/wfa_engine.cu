@@ -966,6 +966,7 @@ struct mwf_b200_batch {
 	long long max_len, max_sbound, arena_full; /* arena_full: the arena when everything that is free is taken */
 	int *d_nseg;
 	uint32_t *d_seqp; /* two- or four-bit packed sequences */
+	uint2 *d_seqp2;   /* the same as overlapping pairs of words */
 	int *d_packed;
 	/* segmented traceback */
 	int seg_P;
@@ -1129,7 +1130,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			return (long long)tl[a] + ql[a] > (long long)tl[c] + ql[c]; });
 	b->seq_bytes = off + 64, b->cigar_words = cw;
 	b->s_limit = (int)std::min<long long>(max_sbound + 1, 0x7ffffff0);
-	b->max_len = max_len, b->max_sbound = max_sbound, b->arena_full = 0, b->d_nseg = 0, b->d_seqp = 0, b->d_packed = 0;
+	b->max_len = max_len, b->max_sbound = max_sbound, b->arena_full = 0, b->d_nseg = 0, b->d_seqp = 0, b->d_seqp2 = 0, b->d_packed = 0;
 	b->seg_P = 0, b->d_snap = 0, b->snap_words = 0, b->d_snapdir = 0, b->snapdir_stride = 0, b->d_nsnap = 0, b->d_sstop = 0, b->h_nsnap = 0, b->d_trace = 0;
 
 	/* kernel family */
@@ -1153,7 +1154,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		G.HL = G.T;
 		G.NT = env_int("MWF_B200_TILE_THREADS", lat ? 512 : 128);
 		G.W = G.CPT * G.NT;
-		G.smem = (size_t)b->tR * G.W * 4 + 64 + sizeof(StepTab) * (size_t)std::max(G.T, 2);
+		G.smem = (size_t)b->tR * G.W * 4 + 64 + sizeof(StepTab) * (size_t)std::max(G.T, 2) + 2 * XCH_BUF;
 		G.fn = 0, G.fn_score = 0, G.grid = 0;
 		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)smem_optin &&
 			(G.W - 2 * G.HL) / 2 - 4 >= 2 * G.HL + n + 8;
@@ -1211,8 +1212,10 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		ws_dev(&b->d_items, sizeof(int2) * b->items_cap, b->dev);
 		ws_dev(&b->d_tmisc, 128, b->dev);
 		if (env_int("MWF_B200_TILE_PACK", 1)) {
-			ws_dev(&b->d_seqp, b->seq_bytes / 2 + 256, b->dev);
+			ws_dev(&b->d_seqp, b->seq_bytes / 2 + (size_t)max_len / 4 + 512, b->dev); /* (slack at the end: the clamped probes of cells off the matrix read up to tl codes past a query) */
 			ws_dev(&b->d_packed, sizeof(int) * std::max(1, n_pairs), b->dev);
+			if (env_int("MWF_B200_TILE_FAST", 2) >= 2 && (long long)b->seq_bytes < (1LL << 28))
+				ws_dev(&b->d_seqp2, 2 * (b->seq_bytes / 2 + (size_t)max_len / 4 + 512), b->dev);
 		}
 		ws_host(&b->h_running, 2 * 64);
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
@@ -1283,7 +1286,7 @@ extern "C" void mwf_b200_batch_upload(mwf_b200_batch_t *b, const char *const *ts
 	CUDA_OK(cudaMemcpyAsync(b->d_order, b->order.data(), sizeof(int) * b->n, cudaMemcpyHostToDevice, b->stream));
 	b->h2d = (int64_t)b->seq_bytes + (int64_t)(sizeof(PairDesc) + sizeof(int)) * b->n;
 	if (b->d_seqp && b->n > 0) { /* two- or four-bit copies for the tile engine's match-run probes */
-		wfa_pack_kernel<<<b->n, 256, 0, b->stream>>>(b->d_seq, b->d_pairs, b->d_seqp, b->d_packed);
+		wfa_pack_kernel<<<b->n, 256, 0, b->stream>>>(b->d_seq, b->d_pairs, b->d_seqp, b->d_seqp2, b->d_packed);
 		CUDA_OK(cudaGetLastError());
 	}
 }
@@ -1379,7 +1382,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	TParams P;
 	memset(&P, 0, sizeof(P));
 	P.pen = b->pen, P.is_tb = b->is_tb, P.max_s = b->opt.max_s, P.max_iter = b->opt.max_iter;
-	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.seqp = b->d_seqp, P.packed = b->d_packed, P.cigar = b->d_cigar;
+	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.seqp = b->d_seqp, P.seqp2 = b->d_seqp2, P.packed = b->d_packed, P.cigar = b->d_cigar;
 	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
 	P.pitch = b->pitch, P.R = b->tR;
 	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32), P.err = (int*)(b->d_tmisc + 40);
@@ -1387,7 +1390,8 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
 	/* (the fast path addresses the sequences by 32-bit bit positions inside the sequence buffer) */
-	P.fast = env_int("MWF_B200_TILE_FAST", 1) && b->pen.e1 <= 2 && b->pen.e2 <= 2 && (long long)b->seq_bytes < (1LL << 28);
+	P.fast = env_int("MWF_B200_TILE_FAST", 2) * (int)(b->pen.e1 <= 2 && b->pen.e2 <= 2 && (long long)b->seq_bytes < (1LL << 28));
+	if (P.fast >= 2 && !b->d_seqp2) P.fast = 1;
 	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
 		const mwf_b200_batch::TileGeom &G = b->geom[g < b->n_geom ? g : 0];
@@ -1713,7 +1717,7 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
 	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
 	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
-	ws_free(b->d_seqp); ws_free(b->d_packed);
+	ws_free(b->d_seqp); ws_free(b->d_seqp2); ws_free(b->d_packed);
 	ws_free(b->d_snap); ws_free(b->d_snapdir); ws_free(b->d_nsnap); ws_free(b->d_sstop); ws_free(b->h_nsnap); ws_free(b->d_trace);
 	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }
 	cudaEventDestroy(b->ev0); cudaEventDestroy(b->ev1);

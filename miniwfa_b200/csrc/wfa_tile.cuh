@@ -67,6 +67,7 @@ struct TParams {
 	PairOut *outs;
 	const uint8_t *seq;
 	const uint32_t *seqp;      /* packed copies (wfa_pack_kernel), word offset = raw byte offset / 8 */
+	const uint2 *seqp2;        /* the same words as overlapping pairs {word i, word i + 1}: one 8-byte load per probe (tile_cells_fast2) */
 	const int *packed;         /* [pair index]: bits per code (2 or 4), 0 when the pair stays on raw bytes */
 	uint32_t *cigar;
 	TileCtl *ctl;              /* [n_pairs] */
@@ -816,6 +817,180 @@ __device__ __forceinline__ int tile_fast_block(const FastCtx &c, const StepTab *
 	return alive_bits;
 }
 
+/*
+ * The same step for pairs on two-bit codes with e1 = 2, e2 = 1 (the default penalties on DNA: the batch workloads), with the
+ * selects of the probe replaced by clamps:
+ *   - the probe position of the target, in bits of the packed buffer, is umin(2 H + c1, position tl): a cell at NEG_INF (2 H wraps to
+ *     a huge unsigned value) or past the end reads position tl -- readable, never used;
+ *   - twice the bases left to the end of the cell's diagonal, lim = kend_j - position, is <= 0 for exactly the cells the reference
+ *     skips (miniwfa.c:402: NEG_INF, k >= tl, d + k >= ql; a cell before the start of its diagonal cannot arise),
+ *     so the run length is min.relu(first differing bit, lim) >> 1: one instruction clamps to the matrix and zeroes the skipped cells;
+ *   - the query is read at (target position) + 2 d + const: for skipped cells that is anywhere in [start of T, end of Q + tl], inside
+ *     the sequence buffer (mwf_b200_batch_create leaves max_len of slack at its end).
+ * The gap rows of the last scores go back to shared memory once, after the loop, instead of under a test in every step.
+ */
+struct Fast2Ctx {
+	uint32_t sb;              /* shared address of this thread's 4 cells in row 0 */
+	uint32_t nbh;             /* lanes 0 / 31: the neighbour's cell in row 0 of the H ring */
+	uint32_t xr, xw;          /* lanes 0 / 31: exchange records read / written in steps of odd t (the other buffer is XCH_BUF bytes on) */
+	bool left, right, edge_lane, bnd_lane;
+	const uint2 *seqw;        /* the packed buffer, as overlapping pairs of words */
+	uint32_t c1, tend, dq0;   /* bit position of T[H + 1] = 2 H + c1; of T[tl]; (bit position of Q[0]) - (of T[0]) + 2 d0 */
+	int kend[4];              /* 2 kmax_j + c1 */
+	int d0;
+};
+
+/* Gap cells across warp boundaries.  The d-1 neighbour of a warp's first cell and the d+1 neighbour of its last belong to other
+ * warps, whose gap rows live in registers.  Lane 31 (E side) and lane 0 (F side) of every warp therefore publish, in every step,
+ * the two gap values their neighbour needs in the NEXT step -- E1 / F1 of the previous score (e1 = 2: the set not written in this
+ * step) and E2 / F2 of this score (e2 = 1) -- as one 8-byte record, double-buffered by the parity of the step; the reader gets
+ * both with one load.  Records: [buffer][warp + 1][side], side 0 = what lane 0 of `warp` reads, side 1 = what its lane 31 reads. */
+#define XCH_BUF ((TILE_MAX_WARPS + 2) * 16)
+#define TILE_MAX_WARPS 16
+
+template<int MODE>
+__device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx &c, const int4 qh, const uint32_t xoff_r, const uint32_t xoff_w, const SeqView &sv,
+                                                 int (&pe1)[4], int (&pf1)[4], const int (&oe1)[4], const int (&of1)[4], int (&pe2)[4], int (&pf2)[4],
+                                                 uint64_t *stepbar, bool wait, uint32_t parity, int (&Hn)[4], uint32_t &tb_out)
+{
+	int ho1[4], ho2[4], hx[4];
+	ldsv<4>(c.sb + qh.y, ho1); ldsv<4>(c.sb + qh.z, ho2); ldsv<4>(c.sb + qh.x, hx);
+	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		A1[j + 1] = max(ho1[j], pe1[j]), A2[j + 1] = max(ho2[j], pe2[j]);
+		C1[j + 1] = max(ho1[j], pf1[j]), C2[j + 1] = max(ho2[j], pf2[j]);
+		if (MODE != MODE_SCORE) bA1[j + 1] = ho1[j] < pe1[j], bA2[j + 1] = ho2[j] < pe2[j], bC1[j + 1] = ho1[j] < pf1[j], bC2[j + 1] = ho2[j] < pf2[j];
+	}
+	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
+	A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
+	C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+	C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	if (MODE != MODE_SCORE) {
+		const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
+		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+	}
+	int h0[4], lim[4];
+	uint32_t tz[4];
+	uint32_t tbw = 0;
+#define FAST2_CELL(j) do { \
+		const int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2] + 1, F2 = C2[j + 2] + 1; \
+		const int e = max(E1, E2), f = max(F1, F2), gmx = max(e, f), hxp = hx[j] + 1; \
+		const int H = max(hxp, gmx); \
+		if (MODE != MODE_SCORE) { \
+			const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4)); \
+			tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j); \
+		} \
+		pe1[j] = E1, pe2[j] = E2, pf1[j] = F1, pf2[j] = F2, h0[j] = H; \
+		const uint32_t tpb = min(((uint32_t)H << 1) + c.c1, c.tend); \
+		const uint32_t qpb = tpb + c.dq0 + 2u * j; \
+		const uint2 tv = __ldg(c.seqw + (tpb >> 5)), qv = __ldg(c.seqw + (qpb >> 5)); \
+		tz[j] = ctz32_sat(__funnelshift_r(tv.x, tv.y, tpb) ^ __funnelshift_r(qv.x, qv.y, qpb)); \
+		lim[j] = c.kend[j] - (int)tpb; \
+	} while (0)
+	FAST2_CELL(1);
+	FAST2_CELL(2);
+	if (wait) mbar_wait(stepbar, parity); /* every warp has finished the previous score */
+	{
+		const int o1 = lds1_if(c.nbh + qh.y, c.edge_lane), o2 = lds1_if(c.nbh + qh.z, c.edge_lane);
+		int x1 = NEG_INF, x2 = NEG_INF;
+		asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q ld.shared.v2.b32 {%0,%1}, [%2]; }" : "+r"(x1), "+r"(x2) : "r"(c.xr + xoff_r), "r"((int)c.edge_lane) : "memory");
+		const int m1 = max(o1, x1), m2 = max(o2, x2);
+		if (c.left) A1[0] = m1, A2[0] = m2;
+		if (c.right) C1[5] = m1, C2[5] = m2;
+		if (MODE != MODE_SCORE) {
+			if (c.left) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
+			if (c.right) bC1[5] = o1 < x1, bC2[5] = o2 < x2;
+		}
+	}
+	FAST2_CELL(0);
+	FAST2_CELL(3);
+#undef FAST2_CELL
+	{ /* what the neighbour warp needs in the next step */
+		const int v1 = c.right ? oe1[3] : of1[0], v2 = c.right ? pe2[3] : pf2[0];
+		asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1,%2}; }" :: "r"(c.xw + xoff_w), "r"(v1), "r"(v2), "r"((int)c.bnd_lane) : "memory");
+	}
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		int m;
+		asm("min.relu.s32 %0, %1, %2;" : "=r"(m) : "r"((int)tz[j]), "r"(lim[j])); /* tz = 0xffffffff (all 16 codes equal) gives 0 here */
+		Hn[j] = h0[j] + (m >> 1);
+	}
+	if ((tz[0] | tz[1] | tz[2] | tz[3]) & 32) { /* rare: some probe matched in all 16 positions */
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+			if (tz[j] == 0xffffffffu && lim[j] > 0) {
+				const int kmax = h0[j] + (lim[j] >> 1), k = min(h0[j] + 16, kmax);
+				Hn[j] = k < kmax ? tile_extend_more(sv, k, c.d0 + j, kmax) : k;
+			}
+	}
+	stsv<4>(c.sb + qh.w, Hn);
+	tb_out = tbw;
+}
+
+/* the cells of a thread that wf_stripe_shrink keeps: any of the five values on the matrix.  H is the largest of the five, so the
+ * other four are looked at only where H itself is off the matrix */
+__device__ __forceinline__ int alive_cells4_h(int d0, int tl, int ql, const int (&H)[4], const int (&E1)[4], const int (&F1)[4], const int (&E2)[4], const int (&F2)[4])
+{
+	int bits = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j)
+		if (on_matrix_u(d0 + j, H[j], tl, ql)) bits |= 1 << j;
+	if (bits != 15) {
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int d = d0 + j;
+			if (on_matrix_u(d, E1[j], tl, ql) || on_matrix_u(d, F1[j], tl, ql) || on_matrix_u(d, E2[j], tl, ql) || on_matrix_u(d, F2[j], tl, ql)) bits |= 1 << j;
+		}
+	}
+	return bits;
+}
+
+template<int MODE>
+__device__ __forceinline__ int tile_fast2_block(const Fast2Ctx &c, const StepTab *tab, const SeqView &sv, uint32_t f1off, uint32_t f2off, int d0, int Tb, int t_alive,
+                                                int tl, int ql, bool useful, uint8_t *tbp, long long tb_pitch, uint64_t *stepbar, uint32_t &step_phase)
+{
+	const int lane = threadIdx.x & 31;
+	int e1a[4], f1a[4], e1b[4], f1b[4], e2a[4], f2a[4], Hn[4];
+	int alive_bits = 0;
+	uint32_t tbw;
+	ldsv<4>(c.sb + tab[0].e.x, e1a); ldsv<4>(c.sb + tab[0].e.x + f1off, f1a); /* E1 / F1 of scores s0 - 1 and s0 */
+	ldsv<4>(c.sb + tab[1].e.x, e1b); ldsv<4>(c.sb + tab[1].e.x + f1off, f1b);
+	ldsv<4>(c.sb + tab[0].e.y, e2a); ldsv<4>(c.sb + tab[0].e.y + f2off, f2a); /* E2 / F2 of score s0 */
+	{ /* what the neighbour warps need in step 1: E1 / F1 of score s0 - 1, E2 / F2 of score s0 */
+		const int v1 = c.right ? e1a[3] : f1a[0], v2 = c.right ? e2a[3] : f2a[0];
+		asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1,%2}; }" :: "r"(c.xw + XCH_BUF), "r"(v1), "r"(v2), "r"((int)c.bnd_lane) : "memory");
+	}
+	__syncthreads();
+#define FAST2_STEP(X1, Y1, O1, P1, XR, XW) do { \
+		tile_cells_fast2<MODE>(c, tab[t - 1].h, XR, XW, sv, X1, Y1, O1, P1, e2a, f2a, stepbar, t > 1, step_phase & 1, Hn, tbw); \
+		if (t > 1) ++step_phase; \
+		if (MODE == MODE_TB) { if (useful) store_tb<4>(tbp, tbw); tbp += tb_pitch; } \
+		if (t > t_alive) alive_bits |= alive_cells4_h(d0, tl, ql, Hn, X1, Y1, e2a, f2a); \
+		if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); } \
+	} while (0)
+	int t = 1;
+	for (;;) { /* odd t: reads the records of buffer 1, writes buffer 0; even t: the other way round */
+		FAST2_STEP(e1a, f1a, e1b, f1b, XCH_BUF, 0);
+		if (++t > Tb) break;
+		FAST2_STEP(e1b, f1b, e1a, f1a, 0, XCH_BUF);
+		if (++t > Tb) break;
+	}
+#undef FAST2_STEP
+	/* the gap rows the next block loads: E1 / F1 of the last two scores, E2 / F2 of the last one */
+	const bool odd = Tb & 1; /* the last step wrote set a */
+	if (odd) {
+		stsv<4>(c.sb + tab[Tb - 1].e.z, e1a); stsv<4>(c.sb + tab[Tb - 1].e.z + f1off, f1a);
+		if (Tb > 1) { stsv<4>(c.sb + tab[Tb - 2].e.z, e1b); stsv<4>(c.sb + tab[Tb - 2].e.z + f1off, f1b); }
+	} else {
+		stsv<4>(c.sb + tab[Tb - 1].e.z, e1b); stsv<4>(c.sb + tab[Tb - 1].e.z + f1off, f1b);
+		stsv<4>(c.sb + tab[Tb - 2].e.z, e1a); stsv<4>(c.sb + tab[Tb - 2].e.z + f1off, f1a);
+	}
+	stsv<4>(c.sb + tab[Tb - 1].e.w, e2a); stsv<4>(c.sb + tab[Tb - 1].e.w + f2off, f2a);
+	return alive_bits;
+}
+
 /* threads per CTA and CTAs per SM the kernel is compiled for: 4 cells per thread keeps the instruction count per cell lowest
  * (batches); 2 and 1 cells per thread put 2x / 4x the threads on a tile, which shortens the dependent chain of one score
  * step when there are too few tiles to fill the GPU (single large pairs) */
@@ -832,6 +1007,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 	int *sc = rows + (size_t)R * W;                          /* [0..2] flags, [3] item */
 	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8), *stepbar = reinterpret_cast<uint64_t*>(sc + 10);
 	StepTab *steptab = reinterpret_cast<StepTab*>(sc + 16); /* [max(T, 2)] row offsets of the steps of the block in flight */
+	const uint32_t xch = smem_u32(steptab + max(P.T, 2)); /* [2][TILE_MAX_WARPS + 2] records of 16 bytes: gap cells across warp boundaries */
 	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
 	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
 	const unsigned int n_items = P.cnt[it & 1].n_items;
@@ -917,7 +1093,25 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 		CellOut<CPT> o;
 		bool stepped = false;
 		if constexpr (CPT == 4) {
-			if (!special && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
+			if (!special && P.fast >= 2 && code_bits == 2 && P.pen.e1 == 2 && P.pen.e2 == 1) { /* interior tile, two-bit codes, default gap extensions */
+				Fast2Ctx c;
+				const uint32_t rb = 4u * W;
+				const int warp = tid >> 5;
+				c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
+				c.edge_lane = (lane == 0 && !no_left) || (lane == 31 && !no_right);
+				c.nbh = sb + (lane == 0 ? -4 : 16);
+				c.xr = xch + 16u * (warp + 1) + (lane == 0 ? 0u : 8u);                    /* side 0: from lane 31 of the warp before; side 1: from lane 0 of the next */
+				c.xw = xch + (lane == 0 ? 16u * warp + 8u : 16u * (warp + 2));           /* lane 0 writes side 1 of the warp before, lane 31 side 0 of the next */
+				c.seqw = P.seqp2;
+				const uint32_t tbits = (uint32_t)(sv.T - P.seqp) << 5, qbits = (uint32_t)(sv.Q - P.seqp) << 5;
+				c.c1 = tbits + 2u, c.tend = tbits + 2u * (uint32_t)tl, c.dq0 = qbits - tbits + 2u * (uint32_t)d0;
+#pragma unroll
+				for (int j = 0; j < 4; ++j) c.kend[j] = 2 * min(tl - 1, ql - 1 - (d0 + j)) + (int)c.c1;
+				c.d0 = d0;
+				alive_bits = tile_fast2_block<MODE>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+				__syncthreads();
+				stepped = true;
+			} else if (!special && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
 				FastCtx c;
 				const uint32_t rb = 4u * W;
 				c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
@@ -1269,7 +1463,7 @@ __global__ void wfa_tile_ckpt_seg_kernel(const TParams P, int j)
  * byte values: a presence bitmap of the pair, codes = rank of the byte among the values present (so equal codes <=> equal bytes),
  * 2 or 4 bits per code, 16 or 8 codes per 32-bit word, position p in bits c(p % (32/c)).  One CTA of 256 threads per pair.
  * Bytes past the end of a sequence become arbitrary codes; the match run is clamped to the matrix anyway. */
-__global__ void __launch_bounds__(256) wfa_pack_kernel(const uint8_t *__restrict__ seq, const PairDesc *__restrict__ pairs, uint32_t *__restrict__ seqp, int *__restrict__ packed)
+__global__ void __launch_bounds__(256) wfa_pack_kernel(const uint8_t *__restrict__ seq, const PairDesc *__restrict__ pairs, uint32_t *__restrict__ seqp, uint2 *__restrict__ seqp2, int *__restrict__ packed)
 {
 	__shared__ unsigned int bm[8];
 	__shared__ unsigned char lut[256];
@@ -1329,6 +1523,15 @@ __global__ void __launch_bounds__(256) wfa_pack_kernel(const uint8_t *__restrict
 			}
 			out[wi] = code;
 		}
+	}
+	if (seqp2 == 0) return;
+	__syncthreads(); /* the words above are visible to the whole CTA: now the overlapping pairs */
+	for (int which = 0; which < 2; ++which) {
+		const long long off = which ? pd.q_off : pd.t_off;
+		const int n_words = ((which ? pd.ql : pd.tl) + cpw - 1) / cpw + 4;
+		const uint32_t *in = seqp + (off >> 3);
+		uint2 *out = seqp2 + (off >> 3);
+		for (int wi = tid; wi < n_words; wi += 256) out[wi] = make_uint2(in[wi], in[wi + 1]);
 	}
 }
 
