@@ -837,14 +837,18 @@ static bool ws_alloc(void **out, size_t bytes, bool host, int dev)
 	bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
 	{
 		std::lock_guard<std::mutex> lk(g_ws_mu);
+		int best = -1; /* best fit: a small request must not take the buffer the next, larger one would have matched */
 		for (size_t i = 0; i < g_ws_free.size(); ++i) {
-			const WsEntry e = g_ws_free[i];
-			if (e.host == host && (host || e.dev == dev) && e.bytes >= bytes && e.bytes <= bytes + bytes / 4 + 65536) {
-				g_ws_free.erase(g_ws_free.begin() + i);
-				g_ws_live[e.p] = e;
-				*out = e.p;
-				return false;
-			}
+			const WsEntry &e = g_ws_free[i];
+			if (e.host == host && (host || e.dev == dev) && e.bytes >= bytes && e.bytes <= bytes + bytes / 4 + 65536 &&
+			    (best < 0 || e.bytes < g_ws_free[best].bytes)) best = (int)i;
+		}
+		if (best >= 0) {
+			const WsEntry e = g_ws_free[best];
+			g_ws_free.erase(g_ws_free.begin() + best);
+			g_ws_live[e.p] = e;
+			*out = e.p;
+			return false;
 		}
 	}
 	void *p = 0;
@@ -889,7 +893,7 @@ static void ws_free(void *p)
 		if (!e.host && e.bytes > cap) drop.push_back(e);
 		else {
 			g_ws_free.push_back(e);
-			while (g_ws_free.size() > 48) { drop.push_back(g_ws_free.front()); g_ws_free.erase(g_ws_free.begin()); }
+			while (g_ws_free.size() > 192) { drop.push_back(g_ws_free.front()); g_ws_free.erase(g_ws_free.begin()); }
 			if (!e.host) {
 				size_t held = 0;
 				for (size_t i = 0; i < g_ws_free.size(); ++i)
@@ -961,7 +965,7 @@ struct mwf_b200_batch {
 	int64_t launches, h2d, d2h;
 	bool ran, timed; /* timed: kernel_ms of the last run has been taken (mwf_b200_batch_wait may be called more than once) */
 	/* tile engine (wfa_tile.cuh) */
-	struct TileGeom { int CPT, NT, T, HL, W, grid; size_t smem; tile_kernel_fn fn, fn_score; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
+	struct TileGeom { int CPT, NT, T, HL, W, grid, grid_p; size_t smem; tile_kernel_fn fn, fn_score; tile_persist_fn pfn, pfn_score; } geom[2]; /* [0] few tiles (latency), [1] many (throughput) */
 	int n_geom, tR, wave_pairs, s_limit;
 	long long max_len, max_sbound, arena_full; /* arena_full: the arena when everything that is free is taken */
 	int *d_nseg;
@@ -980,6 +984,10 @@ struct mwf_b200_batch {
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
 	int2 *d_items;
+	int2 *d_qitems;        /* persistent scheduling: the work queue (payloads, sequence words) */
+	unsigned int *d_qseq;
+	unsigned int q_mask;
+	bool persist;
 	unsigned char *d_tmisc; /* TileCounters[2] @0, n_running @32, arena_used @64 */
 	int *h_running;
 	cudaEvent_t evc[2];
@@ -1051,9 +1059,9 @@ static void alloc_streaming(mwf_b200_batch_t *b)
 /* give the tile engine's workspaces back (the low-memory pass did not fit the arena: the streaming kernels take over) */
 static void free_tile(mwf_b200_batch_t *b)
 {
-	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_qitems); ws_free(b->d_qseq); ws_free(b->d_tmisc); ws_free(b->d_nseg);
 	ws_free(b->d_rowtab); ws_free(b->d_arena); ws_free(b->d_seg);
-	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_tmisc = 0, b->d_nseg = 0, b->d_rowtab = 0, b->d_arena = 0, b->d_seg = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->d_tmisc = 0, b->d_nseg = 0, b->d_rowtab = 0, b->d_arena = 0, b->d_seg = 0;
 	b->arena_total = 0, b->rowtab_stride = 0;
 }
 
@@ -1067,7 +1075,9 @@ static void tile_smem_optin(tile_kernel_fn fn, int dev, int smem_optin)
 	std::lock_guard<std::mutex> lk(mu);
 	for (size_t i = 0; i < done.size(); ++i)
 		if (done[i].first == (void*)fn && done[i].second == dev) return;
-	CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+	cudaFuncAttributes fa;
+	CUDA_OK(cudaFuncGetAttributes(&fa, fn));
+	CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)fa.sharedSizeBytes)); /* (static shared memory counts against the limit) */
 	done.push_back(std::make_pair((void*)fn, dev));
 }
 
@@ -1148,15 +1158,18 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	for (int g = 0; g < b->n_geom; ++g) {
 		mwf_b200_batch::TileGeom &G = b->geom[g];
 		const bool lat = forced ? n_pairs < 16 : g == 0;
-		G.CPT = env_int("MWF_B200_TILE_CPT", lat ? 1 : 4);
+		/* (with the default gap extensions the interior step keeps the gap rows in registers -- tile_cells_fast2 -- and 2 cells per
+		 * thread on 256 threads make the shortest step of a lone tile: 150 kb pair 25.6 ms against 29.0 with 1 x 512) */
+		const bool lean = opt->e1 == 2 && opt->e2 == 1 && env_int("MWF_B200_TILE_FAST", 2) >= 2;
+		G.CPT = env_int("MWF_B200_TILE_CPT", lat ? (lean ? 2 : 1) : 4);
 		if (G.CPT != 1 && G.CPT != 2 && G.CPT != 4) die("MWF_B200_TILE_CPT must be 1, 2 or 4");
 		G.T = std::max(4, std::min(env_int("MWF_B200_TILE_T", lat ? 64 : 32) & ~3, TILE_TMAX));
 		G.HL = G.T;
-		G.NT = env_int("MWF_B200_TILE_THREADS", lat ? 512 : 128);
+		G.NT = env_int("MWF_B200_TILE_THREADS", lat ? (lean ? 256 : 512) : 128);
 		G.W = G.CPT * G.NT;
 		G.smem = (size_t)b->tR * G.W * 4 + 64 + sizeof(StepTab) * (size_t)std::max(G.T, 2) + 2 * XCH_BUF;
 		G.fn = 0, G.fn_score = 0, G.grid = 0;
-		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= 512 && G.W % 4 == 0 && G.smem <= (size_t)smem_optin &&
+		tile_ok = tile_ok && G.NT % 32 == 0 && G.NT >= 64 && G.NT <= TILE_MAX_THREADS(G.CPT) && G.W % 4 == 0 && G.smem + 1024 <= (size_t)smem_optin &&
 			(G.W - 2 * G.HL) / 2 - 4 >= 2 * G.HL + n + 8;
 	}
 	int umax = b->geom[0].W - 2 * b->geom[0].HL, wmax = b->geom[0].W;
@@ -1183,7 +1196,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	ws_dev(&b->d_order, sizeof(int) * std::max(1, n_pairs), b->dev);
 	ws_dev(&b->d_ctl, 64, b->dev);
 	b->d_ring = 0, b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
-	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_tmisc = 0, b->h_running = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->q_mask = 0, b->persist = false, b->d_tmisc = 0, b->h_running = 0;
 	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0, b->wave_pairs = 0;
 	if (b->is_tb) ws_dev(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw), b->dev);
 	if (pref == MWF_B200_KERNEL_TILE) {
@@ -1217,7 +1230,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			if (env_int("MWF_B200_TILE_FAST", 2) >= 2 && (long long)b->seq_bytes < (1LL << 28))
 				ws_dev(&b->d_seqp2, 2 * (b->seq_bytes / 2 + (size_t)max_len / 4 + 512), b->dev);
 		}
-		ws_host(&b->h_running, 2 * 64);
+		ws_host(&b->h_running, 2 * 128);
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
 		if (seg) { /* low-memory mode: checkpoints found by walking a high-memory pass (wfa_tile_checkpoint_kernel) */
@@ -1261,6 +1274,21 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, G.fn, G.NT, G.smem));
 			if (per_sm < 1) die("tile kernel does not fit on an SM");
 			G.grid = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
+			G.pfn = tile_persist_for(b->is_tb, G.CPT);
+			G.pfn_score = tile_persist_for(false, G.CPT);
+			tile_smem_optin((tile_kernel_fn)(void*)G.pfn, b->dev, smem_optin);
+			tile_smem_optin((tile_kernel_fn)(void*)G.pfn_score, b->dev, smem_optin);
+			CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, G.pfn, G.NT, G.smem));
+			if (per_sm < 1) die("tile kernel does not fit on an SM");
+			G.grid_p = b->n_sm * std::min(per_sm, env_int("MWF_B200_TILE_CTAS_PER_SM", 8));
+		}
+		b->persist = env_int("MWF_B200_TILE_PERSIST", 1) != 0;
+		if (b->persist) { /* the work queue: every tile in flight, one plan item per pair, one retire item per CTA, with room to spare */
+			size_t need = 2 * (b->items_cap + (size_t)wp + (size_t)std::max(b->geom[0].grid_p, b->geom[b->n_geom - 1].grid_p)) + 4096, cap = 1;
+			while (cap < need) cap <<= 1;
+			b->q_mask = (unsigned int)(cap - 1);
+			ws_dev(&b->d_qitems, sizeof(int2) * cap, b->dev);
+			ws_dev(&b->d_qseq, sizeof(unsigned int) * cap, b->dev);
 		}
 	} else alloc_streaming(b);
 	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false, b->timed = false;
@@ -1336,8 +1364,11 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
  * The number of running pairs and of tiles per launch is read back one chunk of launches behind, so the device never waits for
  * the host; the tile count picks the geometry of the next chunk. */
 /* returns the error bits the planner raised during the pass: 1 << TS_ARENA, 1 << TS_SHRINK */
+static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j, bool score_kernel);
+
 static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false)
 {
+	if (b->persist) return tile_pass_persist(b, PP, np, seg_j, score_kernel);
 	int err = 0;
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
@@ -1376,6 +1407,41 @@ static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j =
 	return err;
 }
 
+/* the same pass with the persistent kernel: one launch per tile geometry in use instead of two per block of scores.  Batches
+ * run the throughput geometry throughout; a few large pairs start in the latency geometry, and the planner asks for the other
+ * one when the number of tiles in flight crosses `many` (back below many / 2): the pairs park after their block in flight, the
+ * kernel retires, and the host launches the other geometry. */
+static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j, bool score_kernel)
+{
+	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
+	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
+	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]); ++b->launches; }
+	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(PP[0], seg_j); ++b->launches; }
+	CUDA_OK(cudaGetLastError());
+	const bool may_switch = b->n_geom > 1 && np < 16;
+	int g = b->n_geom > 1 && np >= 16 ? 1 : 0;
+	for (int round = 0;; ++round) {
+		TParams P = PP[g];
+		const mwf_b200_batch::TileGeom &G = b->geom[g];
+		P.geom_id = g, P.n_geom = may_switch ? 2 : 1, P.many = env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
+		CUDA_OK(cudaMemsetAsync(b->d_qseq, 0, sizeof(unsigned int) * ((size_t)b->q_mask + 1), b->stream));
+		wfa_tile_persist_begin_kernel<<<1, 256, 0, b->stream>>>(P, G.grid_p);
+		(score_kernel ? G.pfn_score : G.pfn)<<<G.grid_p, G.NT, G.smem, b->stream>>>(P);
+		b->launches += 2;
+		CUDA_OK(cudaGetLastError());
+		int *hr = b->h_running;
+		CUDA_OK(cudaMemcpyAsync(hr, b->d_tmisc, 128, cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaStreamSynchronize(b->stream));
+		const PersistCtl *pq = (const PersistCtl*)(hr + 24);
+		if (env_int("MWF_B200_DEBUG", 0))
+			fprintf(stderr, "[persist dbg] round %d geometry %d: running %d, err %d, head %u tail %u, stop %d -> geometry %d, tiles in flight %d\n",
+			        round, g, hr[8], hr[10], pq->head, pq->tail, pq->stop_req, pq->switch_to, pq->total_tiles);
+		if (hr[8] == 0) return hr[10]; /* n_running, err */
+		if (!may_switch || !pq->stop_req) die("internal error: the persistent tile kernel retired with pairs still running");
+		g = pq->switch_to;
+	}
+}
+
 /* kernel parameters of the tile engine, one set per geometry */
 static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 {
@@ -1385,6 +1451,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.seqp = b->d_seqp, P.seqp2 = b->d_seqp2, P.packed = b->d_packed, P.cigar = b->d_cigar;
 	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
 	P.pitch = b->pitch, P.R = b->tR;
+	P.pq = (PersistCtl*)(b->d_tmisc + 96), P.q_items = b->d_qitems, P.q_seq = b->d_qseq, P.q_mask = b->q_mask;
 	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32), P.err = (int*)(b->d_tmisc + 40);
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
@@ -1716,7 +1783,7 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	ws_free(b->d_seq); ws_free(b->h_seq); ws_free(b->d_pairs); ws_free(b->d_outs); ws_free(b->h_outs);
 	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
 	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
-	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_qitems); ws_free(b->d_qseq); ws_free(b->d_tmisc); ws_free(b->d_nseg);
 	ws_free(b->d_seqp); ws_free(b->d_seqp2); ws_free(b->d_packed);
 	ws_free(b->d_snap); ws_free(b->d_snapdir); ws_free(b->d_nsnap); ws_free(b->d_sstop); ws_free(b->h_nsnap); ws_free(b->d_trace);
 	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }

@@ -40,6 +40,7 @@ enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4, TS_
 
 struct TileCtl { /* per pair, lives in HBM for the whole run */
 	int status, s, wflo, wfhi, cur, last, sid, copied;
+	int tiles_done, pad0_; /* persistent scheduling: tiles of the block in flight that have finished */
 	long long n_iter;
 	/* the block in flight */
 	int Tb, A4, total4, n_tiles;
@@ -51,6 +52,18 @@ struct TileCtl { /* per pair, lives in HBM for the whole run */
 };
 
 struct TileCounters { unsigned int n_items, next; };
+
+/* persistent scheduling (wfa_tile_persist_kernel): one queue of work items per pass, fed by the planner that runs inside the
+ * tile kernel.  An item is (pair, tile) -- or (pair, -1): plan the pair's next block -- or (-1, .): retire.  Consumers take
+ * tickets from `head`; the item of ticket t is published by storing t + 1 into q_seq[t & mask] after its payload. */
+struct PersistCtl {
+	unsigned int head, tail;
+	int n_inflight;    /* pairs with a block in flight (or a plan item queued); 0 => the retire items go out */
+	int stop_req;      /* a planner asked for the other tile geometry: pairs park after their block in flight */
+	int switch_to;
+	int total_tiles;   /* sum of n_tiles over the blocks in flight */
+	int n_start, n_cut; /* pairs in flight when the launch began; blocks cut since (the total above is meaningful once every pair has been cut) */
+};
 
 /* segmented traceback: a snapshot of the ring state every snap_P scores lets the traceback bytes be
  * recomputed one segment of snap_P scores at a time, so a CIGAR never needs s^2 bytes at once */
@@ -88,6 +101,12 @@ struct TParams {
 	int seg_stride, seg_use, step; /* seg_use: this pass collapses the band at the checkpoints (pass 2, miniwfa.c:413-416) */
 	int s_limit;               /* no alignment of the batch can cost more (all-gap bound): a guard against endless runs */
 	int fast;                  /* interior tiles of the 4-cells-per-thread geometry keep the gap rows in registers (tile_cells_fast) */
+	/* persistent scheduling */
+	PersistCtl *pq;
+	int2 *q_items;
+	unsigned int *q_seq;
+	unsigned int q_mask;
+	int geom_id, n_geom, many; /* this launch's geometry (0 latency, 1 throughput); switch above `many` / below many / 2 tiles in flight */
 	/* segmented traceback */
 	int snap_P, snapdir_stride, snap_take; /* snap_take: save a snapshot whenever s is a multiple of snap_P (a multiple of 256) */
 	int32_t *snap_arena;
@@ -171,7 +190,7 @@ __global__ void wfa_tile_init_kernel(const TParams P)
 		st[doff] = k; /* H of score 0 lives in slot 0 */
 		TileCtl *c = P.ctl + slot;
 		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = 0;
-		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1;
+		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1, c->tiles_done = 0;
 		c->status = (k == pd.tl - 1 && k == pd.ql - 1) ? TS_DONE : TS_RUN;
 		if (c->status == TS_DONE) {
 			PairOut o;
@@ -186,36 +205,65 @@ __global__ void wfa_tile_init_kernel(const TParams P)
 /* between blocks: replay the finished block, trim, cut the next one                            */
 /* ------------------------------------------------------------------------------------------ */
 
-__global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
+/* queue helpers of the persistent scheduler */
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p)
+{
+	unsigned int v;
+	asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_volatile_u32(unsigned int *p, unsigned int v)
+{
+	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+/* publish item `ticket`: payload, fence, then the sequence word the consumer spins on */
+__device__ __forceinline__ void q_publish(const TParams &P, unsigned int ticket, int pair, int tile)
+{
+	const unsigned int i = ticket & P.q_mask;
+	__stcg(P.q_items + i, make_int2(pair, tile));
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(P.q_seq + i), "r"(ticket + 1u) : "memory"); /* (a release, not __threadfence(): that one also drops the SM's L1) */
+}
+
+/* The planner of one pair: replay the block that has just finished, trim, cut the next block and hand out its tiles.
+ * PERSIST = false: wfa_plan_kernel, one CTA per pair between two launches of the tile kernel, tiles appended to the item list
+ * of launch `it`.  PERSIST = true: called inside wfa_tile_persist_kernel by the CTA that finished the last tile of the pair's
+ * block (or took the pair's plan item); tiles go to the queue; `retire` is set when the last pair in flight has ended or
+ * parked, and the caller then publishes the retire items.  All threads of the CTA must call it. */
+template<bool PERSIST>
+__device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *retire)
 {
 	__shared__ int sh[4];
-	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	__shared__ int widths[TILE_TMAX];
+	__shared__ long long sh_row[2];
+	__shared__ int sh_emit[4]; /* items base, n_tiles, first score of the rows, number of rows */
+	const int pi = P.order[P.pair0 + slot];
 	TileCtl *c = P.ctl + slot;
-	if (blockIdx.x == 0 && threadIdx.x == 0) { P.cnt[(it + 1) & 1].n_items = 0; P.cnt[(it + 1) & 1].next = 0; }
-	if (c->status != TS_RUN) return;
+#define CL(f) __ldcg(&c->f) /* TileCtl is written by other SMs inside the persistent kernel: read it from L2 */
+	__syncthreads(); /* (the shared words above may still be read by the previous call) */
+	if (CL(status) != TS_RUN) return;
 	const PairDesc pd = P.pairs[pi];
 	const int tl = pd.tl, ql = pd.ql, n = P.pen.nring, doff = tile_doff(P, tl);
-	int status = TS_RUN, s = c->s, wflo = c->wflo, wfhi = c->wfhi;
-	if (c->Tb > 0) { /* replay, in the order of miniwfa.c:419-426 */
-		__shared__ int widths[TILE_TMAX];
-		if (threadIdx.x < c->Tb) widths[threadIdx.x] = c->hi_log[threadIdx.x] - c->lo_log[threadIdx.x] + 1; /* all loads in flight at once */
+	int status = TS_RUN, s = CL(s), wflo = CL(wflo), wfhi = CL(wfhi);
+	const int Tb_done = CL(Tb);
+	if (Tb_done > 0) { /* replay, in the order of miniwfa.c:419-426 */
+		if (threadIdx.x < Tb_done) widths[threadIdx.x] = CL(hi_log[threadIdx.x]) - CL(lo_log[threadIdx.x]) + 1; /* all loads in flight at once */
 		__syncthreads();
 		if (threadIdx.x == 0) {
-			long long n_iter = c->n_iter;
-			const int Tb = c->Tb, s0 = c->s, done_t = c->done_t;
+			long long n_iter = CL(n_iter);
+			const int Tb = Tb_done, s0 = s, done_t = CL(done_t);
 			int last = 0;
 			for (int t = 1; t <= Tb; ++t) {
 				n_iter += widths[t - 1];
 				s = s0 + t;
 				if ((P.max_iter > 0 && n_iter > P.max_iter) || (P.max_s > 0 && s > P.max_s)) { status = TS_STOPPED; break; }
-				if (done_t == t) { status = TS_DONE; last = c->done_last; break; }
+				if (done_t == t) { status = TS_DONE; last = CL(done_last); break; }
 			}
 			c->n_iter = n_iter, c->s = s, c->last = last;
-			c->wflo = c->fin_lo, c->wfhi = c->fin_hi, c->cur ^= 1;
+			c->wflo = CL(fin_lo), c->wfhi = CL(fin_hi), c->cur = CL(cur) ^ 1;
 			sh[0] = status, sh[1] = s;
 		}
 		__syncthreads();
-		status = sh[0], s = sh[1], wflo = c->fin_lo, wfhi = c->fin_hi;
+		status = sh[0], s = sh[1], wflo = CL(fin_lo), wfhi = CL(fin_hi);
 		__syncthreads();
 		if (status == TS_RUN && (s & 0xff) == 0) { /* wf_stripe_shrink (:144-171) from the tiles' alive words */
 			const int32_t *alive = P.alive + (size_t)slot * P.pitch + doff;
@@ -224,13 +272,13 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 				int nl = wfhi + 1;
 				for (int base = wflo; base <= wfhi; base += 32) {
 					const int d = base + lane;
-					const unsigned m = __ballot_sync(0xffffffffu, d <= wfhi && alive[d] == tag);
+					const unsigned m = __ballot_sync(0xffffffffu, d <= wfhi && __ldcg(alive + d) == tag);
 					if (m) { nl = base + __ffs(m) - 1; break; }
 				}
 				int nh = nl - 1;
 				for (int base = wfhi; base >= nl; base -= 32) {
 					const int d = base - lane;
-					const unsigned m = __ballot_sync(0xffffffffu, d >= nl && alive[d] == tag);
+					const unsigned m = __ballot_sync(0xffffffffu, d >= nl && __ldcg(alive + d) == tag);
 					if (m) { nh = base - (__ffs(m) - 1); break; }
 				}
 				if (lane == 0) sh[2] = nl, sh[3] = nh;
@@ -241,19 +289,24 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			else wflo = nl, wfhi = nh;
 		}
 	}
-	__shared__ long long sh_row[2];
-	__shared__ int sh_emit[4]; /* items base, n_tiles, first score of the rows, number of rows */
 	if (threadIdx.x == 0) sh_emit[1] = 0, sh_emit[3] = 0;
 	__syncthreads();
 	if (threadIdx.x == 0) {
+	bool park = false;
 	if (status == TS_RUN && s > P.s_limit) status = TS_SHRINK; /* cannot happen: the all-gap alignment costs less */
 	if (status == TS_RUN && P.s_stop && s >= P.s_stop[slot]) status = TS_SEGEND; /* end of a traceback segment */
-	if (status == TS_RUN) { /* cut the next block */
-		int sid = c->sid, Tb, copy_only = 0;
+	if (PERSIST && status == TS_RUN && *(volatile int*)&P.pq->stop_req) { /* the other tile geometry takes over: the next launch cuts the block */
+		park = true;
+		c->wflo = wflo, c->wfhi = wfhi;
+		atomicSub(&P.pq->total_tiles, CL(n_tiles));
+		c->Tb = 0, c->n_tiles = 0;
+	}
+	if (status == TS_RUN && !park) { /* cut the next block */
+		int sid = CL(sid), Tb, copy_only = 0;
 		const int n_seg = P.seg_use ? P.n_seg[slot] : 0;
 		const int *seg = P.seg + (size_t)slot * P.seg_stride;
 		if (sid < n_seg && seg[2 * sid] == s) { /* band collapse (:413-416) */
-			if (!c->copied) copy_only = 1, c->copied = 1; /* first bring both state buffers to the same contents: the narrow blocks
+			if (!CL(copied)) copy_only = 1, c->copied = 1; /* first bring both state buffers to the same contents: the narrow blocks
 			                                                  that follow store only their own columns, but still read the wide slices */
 			else {
 				wflo = wfhi = seg[2 * sid + 1];
@@ -288,38 +341,64 @@ __global__ void __launch_bounds__(128) wfa_plan_kernel(const TParams P, int it)
 			if (k >= P.snapdir_stride || (long long)off + words > P.snap_cap) status = TS_ARENA;
 			else {
 				SnapDir d;
-				d.s = s, d.wflo = wflo, d.wfhi = wfhi, d.A4 = A4, d.rowsize = rowsize, d.pad = 0, d.off = (long long)off, d.n_iter = c->n_iter;
+				d.s = s, d.wflo = wflo, d.wfhi = wfhi, d.A4 = A4, d.rowsize = rowsize, d.pad = 0, d.off = (long long)off, d.n_iter = CL(n_iter);
 				P.snapdir[(size_t)slot * P.snapdir_stride + k] = d;
 				P.n_snap[slot] = k + 1;
 				c->snap_off = (long long)off, c->snap_rowsize = rowsize;
 			}
 		}
 		if (status == TS_RUN) {
+			const int old_tiles = CL(n_tiles);
 			c->wflo = wflo, c->wfhi = wfhi, c->sid = sid;
 			c->Tb = Tb, c->A4 = A4, c->total4 = total4, c->n_tiles = n_tiles;
-			c->done_t = 0x7fffffff, c->done_last = 0;
-			sh_emit[0] = (int)atomicAdd(&P.cnt[it & 1].n_items, (unsigned int)n_tiles), sh_emit[1] = n_tiles;
+			c->done_t = 0x7fffffff, c->done_last = 0, c->tiles_done = 0;
+			if (PERSIST) {
+				sh_emit[0] = (int)atomicAdd(&P.pq->tail, (unsigned int)n_tiles), sh_emit[1] = n_tiles;
+				const int tot = atomicAdd(&P.pq->total_tiles, n_tiles - old_tiles) + n_tiles - old_tiles;
+				const int n_cut = P.n_geom > 1 ? atomicAdd(&P.pq->n_cut, 1) + 1 : 0;
+				if (P.n_geom > 1 && n_cut >= *(volatile int*)&P.pq->n_start && ((P.geom_id == 0 && tot >= P.many) || (P.geom_id == 1 && tot < P.many / 2)) && !*(volatile int*)&P.pq->stop_req) {
+					P.pq->switch_to = P.geom_id ^ 1;
+					__threadfence();
+					*(volatile int*)&P.pq->stop_req = 1;
+				}
+			} else sh_emit[0] = (int)atomicAdd(&P.cnt[it & 1].n_items, (unsigned int)n_tiles), sh_emit[1] = n_tiles;
 		}
 	}
 	if (status != TS_RUN) {
 		c->status = status;
 		if (status == TS_ARENA || status == TS_SHRINK) atomicOr(P.err, 1 << status);
 		atomicSub(P.n_running, 1);
+		if (PERSIST) atomicSub(&P.pq->total_tiles, CL(n_tiles));
 		if (status != TS_SEGEND) { /* (a segment's end leaves the result record to the pass that reaches the end) */
 			PairOut o;
-			o.s = status == TS_DONE ? c->s : -1;
-			o.n_cigar = 0, o.n_iter = c->n_iter, o.cigar_pos = pd.cigar_off + pd.cigar_cap;
+			o.s = status == TS_DONE ? CL(s) : -1;
+			o.n_cigar = 0, o.n_iter = CL(n_iter), o.cigar_pos = pd.cigar_off + pd.cigar_cap;
 			o.status = status == TS_DONE ? ST_OK : status == TS_STOPPED ? ST_STOPPED : status == TS_ARENA ? ST_ARENA : ST_SHRINK;
 			o.pad_ = 0;
 			o.end_s = 0, o.end_i = 0, o.end_k = 0, o.pad2_ = 0;
 			P.outs[pi] = o;
 		}
 	}
+	if (PERSIST && (status != TS_RUN || park)) { /* this pair has no block in flight any more */
+		__threadfence();
+		if (atomicSub(&P.pq->n_inflight, 1) == 1) *retire = 1;
+	}
 	} /* thread 0 */
 	__syncthreads();
-	for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) P.items[sh_emit[0] + j] = make_int2(slot, j); /* the block's tiles */
+	if (PERSIST) {
+		for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) q_publish(P, (unsigned int)sh_emit[0] + j, slot, j); /* the block's tiles */
+	} else {
+		for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) P.items[sh_emit[0] + j] = make_int2(slot, j);
+	}
 	if (threadIdx.x < sh_emit[3]) /* wf_tb_add (:33-44): where the traceback row of every score of the block starts */
 		P.rowtab[(size_t)slot * P.rowtab_stride + sh_emit[2] + 1 + threadIdx.x] = sh_row[0] + (long long)threadIdx.x * sh_row[1];
+}
+#undef CL
+
+__global__ void __launch_bounds__(128) wfa_plan_kernel(const __grid_constant__ TParams P, int it)
+{
+	if (blockIdx.x == 0 && threadIdx.x == 0) { P.cnt[(it + 1) & 1].n_items = 0; P.cnt[(it + 1) & 1].next = 0; }
+	plan_pair<false>(P, blockIdx.x, it, 0);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -829,14 +908,14 @@ __device__ __forceinline__ int tile_fast_block(const FastCtx &c, const StepTab *
  *     the sequence buffer (mwf_b200_batch_create leaves max_len of slack at its end).
  * The gap rows of the last scores go back to shared memory once, after the loop, instead of under a test in every step.
  */
-struct Fast2Ctx {
-	uint32_t sb;              /* shared address of this thread's 4 cells in row 0 */
+template<int CPT> struct Fast2Ctx {
+	uint32_t sb;              /* shared address of this thread's cells in row 0 */
 	uint32_t nbh;             /* lanes 0 / 31: the neighbour's cell in row 0 of the H ring */
 	uint32_t xr, xw;          /* lanes 0 / 31: exchange records read / written in steps of odd t (the other buffer is XCH_BUF bytes on) */
 	bool left, right, edge_lane, bnd_lane;
 	const uint2 *seqw;        /* the packed buffer, as overlapping pairs of words */
-	uint32_t c1, tend, dq0;   /* bit position of T[H + 1] = 2 H + c1; of T[tl]; (bit position of Q[0]) - (of T[0]) + 2 d0 */
-	int kend[4];              /* 2 kmax_j + c1 */
+	uint32_t c1, tend, dq0;   /* bit position of T[H + 1] = cb H + c1 (cb = bits per code); of T[tl]; (bit position of Q[0]) - (of T[0]) + cb d0 */
+	int kend[CPT];            /* cb kmax_j + c1 */
 	int d0;
 };
 
@@ -845,34 +924,38 @@ struct Fast2Ctx {
  * the two gap values their neighbour needs in the NEXT step -- E1 / F1 of the previous score (e1 = 2: the set not written in this
  * step) and E2 / F2 of this score (e2 = 1) -- as one 8-byte record, double-buffered by the parity of the step; the reader gets
  * both with one load.  Records: [buffer][warp + 1][side], side 0 = what lane 0 of `warp` reads, side 1 = what its lane 31 reads. */
-#define XCH_BUF ((TILE_MAX_WARPS + 2) * 16)
 #define TILE_MAX_WARPS 16
+#define XCH_BUF ((TILE_MAX_WARPS + 2) * 16)
 
-template<int MODE>
-__device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx &c, const int4 qh, const uint32_t xoff_r, const uint32_t xoff_w, const SeqView &sv,
-                                                 int (&pe1)[4], int (&pf1)[4], const int (&oe1)[4], const int (&of1)[4], int (&pe2)[4], int (&pf2)[4],
-                                                 uint64_t *stepbar, bool wait, uint32_t parity, int (&Hn)[4], uint32_t &tb_out)
+/* LCB = log2(bits per code): 1 for two-bit codes (DNA), 2 for four-bit codes (DNA with N, soft-masked, IUPAC).  CPT = 4 is the
+ * throughput geometry (cells 1 and 2 of a thread need nothing from other warps and go before the step barrier's wait); CPT = 2
+ * and 1 put more warps on a tile, for single large pairs. */
+template<int MODE, int CPT, int LCB>
+__device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const int4 qh, const uint32_t xoff_r, const uint32_t xoff_w, const SeqView &sv,
+                                                 int (&pe1)[CPT], int (&pf1)[CPT], const int (&oe1)[CPT], const int (&of1)[CPT], int (&pe2)[CPT], int (&pf2)[CPT],
+                                                 uint64_t *stepbar, bool wait, uint32_t parity, int (&Hn)[CPT], uint32_t &tb_out)
 {
-	int ho1[4], ho2[4], hx[4];
-	ldsv<4>(c.sb + qh.y, ho1); ldsv<4>(c.sb + qh.z, ho2); ldsv<4>(c.sb + qh.x, hx);
-	int A1[6], A2[6], C1[6], C2[6], bA1[6], bA2[6], bC1[6], bC2[6];
+	constexpr uint32_t CB = 1u << LCB;
+	int ho1[CPT], ho2[CPT], hx[CPT];
+	ldsv<CPT>(c.sb + qh.y, ho1); ldsv<CPT>(c.sb + qh.z, ho2); ldsv<CPT>(c.sb + qh.x, hx);
+	int A1[CPT + 2], A2[CPT + 2], C1[CPT + 2], C2[CPT + 2], bA1[CPT + 2], bA2[CPT + 2], bC1[CPT + 2], bC2[CPT + 2];
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
+	for (int j = 0; j < CPT; ++j) {
 		A1[j + 1] = max(ho1[j], pe1[j]), A2[j + 1] = max(ho2[j], pe2[j]);
 		C1[j + 1] = max(ho1[j], pf1[j]), C2[j + 1] = max(ho2[j], pf2[j]);
 		if (MODE != MODE_SCORE) bA1[j + 1] = ho1[j] < pe1[j], bA2[j + 1] = ho2[j] < pe2[j], bC1[j + 1] = ho1[j] < pf1[j], bC2[j + 1] = ho2[j] < pf2[j];
 	}
-	A1[0] = __shfl_up_sync(0xffffffffu, A1[4], 1);
-	A2[0] = __shfl_up_sync(0xffffffffu, A2[4], 1);
-	C1[5] = __shfl_down_sync(0xffffffffu, C1[1], 1);
-	C2[5] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	A1[0] = __shfl_up_sync(0xffffffffu, A1[CPT], 1);
+	A2[0] = __shfl_up_sync(0xffffffffu, A2[CPT], 1);
+	C1[CPT + 1] = __shfl_down_sync(0xffffffffu, C1[1], 1);
+	C2[CPT + 1] = __shfl_down_sync(0xffffffffu, C2[1], 1);
 	if (MODE != MODE_SCORE) {
-		const int bl = __shfl_up_sync(0xffffffffu, bA1[4] | bA2[4] << 1, 1);
+		const int bl = __shfl_up_sync(0xffffffffu, bA1[CPT] | bA2[CPT] << 1, 1);
 		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
-		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[5] = br & 1, bC2[5] = br >> 1;
+		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[CPT + 1] = br & 1, bC2[CPT + 1] = br >> 1;
 	}
-	int h0[4], lim[4];
-	uint32_t tz[4];
+	int h0[CPT], lim[CPT];
+	uint32_t tz[CPT];
 	uint32_t tbw = 0;
 #define FAST2_CELL(j) do { \
 		const int E1 = A1[j], E2 = A2[j], F1 = C1[j + 2] + 1, F2 = C2[j + 2] + 1; \
@@ -883,14 +966,13 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx &c, const int4 q
 			tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j); \
 		} \
 		pe1[j] = E1, pe2[j] = E2, pf1[j] = F1, pf2[j] = F2, h0[j] = H; \
-		const uint32_t tpb = min(((uint32_t)H << 1) + c.c1, c.tend); \
-		const uint32_t qpb = tpb + c.dq0 + 2u * j; \
+		const uint32_t tpb = min(((uint32_t)H << LCB) + c.c1, c.tend); \
+		const uint32_t qpb = tpb + c.dq0 + CB * j; \
 		const uint2 tv = __ldg(c.seqw + (tpb >> 5)), qv = __ldg(c.seqw + (qpb >> 5)); \
 		tz[j] = ctz32_sat(__funnelshift_r(tv.x, tv.y, tpb) ^ __funnelshift_r(qv.x, qv.y, qpb)); \
 		lim[j] = c.kend[j] - (int)tpb; \
 	} while (0)
-	FAST2_CELL(1);
-	FAST2_CELL(2);
+	if (CPT == 4) { FAST2_CELL(1); FAST2_CELL(2); }
 	if (wait) mbar_wait(stepbar, parity); /* every warp has finished the previous score */
 	{
 		const int o1 = lds1_if(c.nbh + qh.y, c.edge_lane), o2 = lds1_if(c.nbh + qh.z, c.edge_lane);
@@ -898,48 +980,54 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx &c, const int4 q
 		asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q ld.shared.v2.b32 {%0,%1}, [%2]; }" : "+r"(x1), "+r"(x2) : "r"(c.xr + xoff_r), "r"((int)c.edge_lane) : "memory");
 		const int m1 = max(o1, x1), m2 = max(o2, x2);
 		if (c.left) A1[0] = m1, A2[0] = m2;
-		if (c.right) C1[5] = m1, C2[5] = m2;
+		if (c.right) C1[CPT + 1] = m1, C2[CPT + 1] = m2;
 		if (MODE != MODE_SCORE) {
 			if (c.left) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
-			if (c.right) bC1[5] = o1 < x1, bC2[5] = o2 < x2;
+			if (c.right) bC1[CPT + 1] = o1 < x1, bC2[CPT + 1] = o2 < x2;
 		}
 	}
-	FAST2_CELL(0);
-	FAST2_CELL(3);
+	if (CPT == 4) { FAST2_CELL(0); FAST2_CELL((CPT - 1)); }
+	else {
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) FAST2_CELL(j);
+	}
 #undef FAST2_CELL
 	{ /* what the neighbour warp needs in the next step */
-		const int v1 = c.right ? oe1[3] : of1[0], v2 = c.right ? pe2[3] : pf2[0];
+		const int v1 = c.right ? oe1[CPT - 1] : of1[0], v2 = c.right ? pe2[CPT - 1] : pf2[0];
 		asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1,%2}; }" :: "r"(c.xw + xoff_w), "r"(v1), "r"(v2), "r"((int)c.bnd_lane) : "memory");
 	}
+	uint32_t any = 0;
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
+	for (int j = 0; j < CPT; ++j) {
 		int m;
-		asm("min.relu.s32 %0, %1, %2;" : "=r"(m) : "r"((int)tz[j]), "r"(lim[j])); /* tz = 0xffffffff (all 16 codes equal) gives 0 here */
-		Hn[j] = h0[j] + (m >> 1);
+		asm("min.relu.s32 %0, %1, %2;" : "=r"(m) : "r"((int)tz[j]), "r"(lim[j])); /* tz = 0xffffffff (all codes of the word equal) gives 0 here */
+		Hn[j] = h0[j] + (m >> LCB);
+		any |= tz[j];
 	}
-	if ((tz[0] | tz[1] | tz[2] | tz[3]) & 32) { /* rare: some probe matched in all 16 positions */
+	if (any & 32) { /* rare: some probe matched in all its positions */
 #pragma unroll
-		for (int j = 0; j < 4; ++j)
+		for (int j = 0; j < CPT; ++j)
 			if (tz[j] == 0xffffffffu && lim[j] > 0) {
-				const int kmax = h0[j] + (lim[j] >> 1), k = min(h0[j] + 16, kmax);
+				const int kmax = h0[j] + (lim[j] >> LCB), k = min(h0[j] + (32 >> LCB), kmax);
 				Hn[j] = k < kmax ? tile_extend_more(sv, k, c.d0 + j, kmax) : k;
 			}
 	}
-	stsv<4>(c.sb + qh.w, Hn);
+	stsv<CPT>(c.sb + qh.w, Hn);
 	tb_out = tbw;
 }
 
 /* the cells of a thread that wf_stripe_shrink keeps: any of the five values on the matrix.  H is the largest of the five, so the
  * other four are looked at only where H itself is off the matrix */
-__device__ __forceinline__ int alive_cells4_h(int d0, int tl, int ql, const int (&H)[4], const int (&E1)[4], const int (&F1)[4], const int (&E2)[4], const int (&F2)[4])
+template<int CPT>
+__device__ __forceinline__ int alive_cells_h(int d0, int tl, int ql, const int (&H)[CPT], const int (&E1)[CPT], const int (&F1)[CPT], const int (&E2)[CPT], const int (&F2)[CPT])
 {
 	int bits = 0;
 #pragma unroll
-	for (int j = 0; j < 4; ++j)
+	for (int j = 0; j < CPT; ++j)
 		if (on_matrix_u(d0 + j, H[j], tl, ql)) bits |= 1 << j;
-	if (bits != 15) {
+	if (bits != (1 << CPT) - 1) {
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
+		for (int j = 0; j < CPT; ++j) {
 			const int d = d0 + j;
 			if (on_matrix_u(d, E1[j], tl, ql) || on_matrix_u(d, F1[j], tl, ql) || on_matrix_u(d, E2[j], tl, ql) || on_matrix_u(d, F2[j], tl, ql)) bits |= 1 << j;
 		}
@@ -947,27 +1035,27 @@ __device__ __forceinline__ int alive_cells4_h(int d0, int tl, int ql, const int 
 	return bits;
 }
 
-template<int MODE>
-__device__ __forceinline__ int tile_fast2_block(const Fast2Ctx &c, const StepTab *tab, const SeqView &sv, uint32_t f1off, uint32_t f2off, int d0, int Tb, int t_alive,
+template<int MODE, int CPT, int LCB>
+__device__ __forceinline__ int tile_fast2_block(const Fast2Ctx<CPT> &c, const StepTab *tab, const SeqView &sv, uint32_t f1off, uint32_t f2off, int d0, int Tb, int t_alive,
                                                 int tl, int ql, bool useful, uint8_t *tbp, long long tb_pitch, uint64_t *stepbar, uint32_t &step_phase)
 {
 	const int lane = threadIdx.x & 31;
-	int e1a[4], f1a[4], e1b[4], f1b[4], e2a[4], f2a[4], Hn[4];
+	int e1a[CPT], f1a[CPT], e1b[CPT], f1b[CPT], e2a[CPT], f2a[CPT], Hn[CPT];
 	int alive_bits = 0;
 	uint32_t tbw;
-	ldsv<4>(c.sb + tab[0].e.x, e1a); ldsv<4>(c.sb + tab[0].e.x + f1off, f1a); /* E1 / F1 of scores s0 - 1 and s0 */
-	ldsv<4>(c.sb + tab[1].e.x, e1b); ldsv<4>(c.sb + tab[1].e.x + f1off, f1b);
-	ldsv<4>(c.sb + tab[0].e.y, e2a); ldsv<4>(c.sb + tab[0].e.y + f2off, f2a); /* E2 / F2 of score s0 */
+	ldsv<CPT>(c.sb + tab[0].e.x, e1a); ldsv<CPT>(c.sb + tab[0].e.x + f1off, f1a); /* E1 / F1 of scores s0 - 1 and s0 */
+	ldsv<CPT>(c.sb + tab[1].e.x, e1b); ldsv<CPT>(c.sb + tab[1].e.x + f1off, f1b);
+	ldsv<CPT>(c.sb + tab[0].e.y, e2a); ldsv<CPT>(c.sb + tab[0].e.y + f2off, f2a); /* E2 / F2 of score s0 */
 	{ /* what the neighbour warps need in step 1: E1 / F1 of score s0 - 1, E2 / F2 of score s0 */
-		const int v1 = c.right ? e1a[3] : f1a[0], v2 = c.right ? e2a[3] : f2a[0];
+		const int v1 = c.right ? e1a[CPT - 1] : f1a[0], v2 = c.right ? e2a[CPT - 1] : f2a[0];
 		asm volatile("{ .reg .pred q; setp.ne.s32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1,%2}; }" :: "r"(c.xw + XCH_BUF), "r"(v1), "r"(v2), "r"((int)c.bnd_lane) : "memory");
 	}
 	__syncthreads();
 #define FAST2_STEP(X1, Y1, O1, P1, XR, XW) do { \
-		tile_cells_fast2<MODE>(c, tab[t - 1].h, XR, XW, sv, X1, Y1, O1, P1, e2a, f2a, stepbar, t > 1, step_phase & 1, Hn, tbw); \
+		tile_cells_fast2<MODE, CPT, LCB>(c, tab[t - 1].h, XR, XW, sv, X1, Y1, O1, P1, e2a, f2a, stepbar, t > 1, step_phase & 1, Hn, tbw); \
 		if (t > 1) ++step_phase; \
-		if (MODE == MODE_TB) { if (useful) store_tb<4>(tbp, tbw); tbp += tb_pitch; } \
-		if (t > t_alive) alive_bits |= alive_cells4_h(d0, tl, ql, Hn, X1, Y1, e2a, f2a); \
+		if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, tbw); tbp += tb_pitch; } \
+		if (t > t_alive) alive_bits |= alive_cells_h<CPT>(d0, tl, ql, Hn, X1, Y1, e2a, f2a); \
 		if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); } \
 	} while (0)
 	int t = 1;
@@ -981,237 +1069,367 @@ __device__ __forceinline__ int tile_fast2_block(const Fast2Ctx &c, const StepTab
 	/* the gap rows the next block loads: E1 / F1 of the last two scores, E2 / F2 of the last one */
 	const bool odd = Tb & 1; /* the last step wrote set a */
 	if (odd) {
-		stsv<4>(c.sb + tab[Tb - 1].e.z, e1a); stsv<4>(c.sb + tab[Tb - 1].e.z + f1off, f1a);
-		if (Tb > 1) { stsv<4>(c.sb + tab[Tb - 2].e.z, e1b); stsv<4>(c.sb + tab[Tb - 2].e.z + f1off, f1b); }
+		stsv<CPT>(c.sb + tab[Tb - 1].e.z, e1a); stsv<CPT>(c.sb + tab[Tb - 1].e.z + f1off, f1a);
+		if (Tb > 1) { stsv<CPT>(c.sb + tab[Tb - 2].e.z, e1b); stsv<CPT>(c.sb + tab[Tb - 2].e.z + f1off, f1b); }
 	} else {
-		stsv<4>(c.sb + tab[Tb - 1].e.z, e1b); stsv<4>(c.sb + tab[Tb - 1].e.z + f1off, f1b);
-		stsv<4>(c.sb + tab[Tb - 2].e.z, e1a); stsv<4>(c.sb + tab[Tb - 2].e.z + f1off, f1a);
+		stsv<CPT>(c.sb + tab[Tb - 1].e.z, e1b); stsv<CPT>(c.sb + tab[Tb - 1].e.z + f1off, f1b);
+		stsv<CPT>(c.sb + tab[Tb - 2].e.z, e1a); stsv<CPT>(c.sb + tab[Tb - 2].e.z + f1off, f1a);
 	}
-	stsv<4>(c.sb + tab[Tb - 1].e.w, e2a); stsv<4>(c.sb + tab[Tb - 1].e.w + f2off, f2a);
+	stsv<CPT>(c.sb + tab[Tb - 1].e.w, e2a); stsv<CPT>(c.sb + tab[Tb - 1].e.w + f2off, f2a);
 	return alive_bits;
 }
 
 /* threads per CTA and CTAs per SM the kernel is compiled for: 4 cells per thread keeps the instruction count per cell lowest
  * (batches); 2 and 1 cells per thread put 2x / 4x the threads on a tile, which shortens the dependent chain of one score
  * step when there are too few tiles to fill the GPU (single large pairs) */
-#define TILE_MAX_THREADS(CPT) 512
+#define TILE_MAX_THREADS(CPT) ((CPT) == 2 ? 256 : 512)
 #define TILE_MIN_CTAS(CPT) ((CPT) == 4 ? 1 : 2)
 
-/* shared memory: rows[R][W] int32 | ctl ints [16] (flags, item, mbarrier) */
+/* the persistent CTA state of the tile kernels: shared-memory layout and the phases of the two mbarriers */
+struct TileSmem {
+	int32_t *rows;        /* [R][W] */
+	int *sc;              /* [0..2] flags, [3..5] item */
+	uint64_t *bar, *stepbar;
+	StepTab *steptab;     /* [max(T, 2)] row offsets of the steps of the block in flight */
+	uint32_t xch;         /* [2][TILE_MAX_WARPS + 2] records of 16 bytes: gap cells across warp boundaries */
+	uint32_t sb;          /* shared address of this thread's cells in row 0 */
+	uint32_t phase, step_phase;
+};
+
+template<int CPT>
+__device__ __forceinline__ void tile_smem_setup(const TParams &P, int32_t *smem_tile, TileSmem &S)
+{
+	const int tid = threadIdx.x;
+	S.rows = smem_tile;
+	S.sc = S.rows + (size_t)P.R * P.W;
+	S.bar = reinterpret_cast<uint64_t*>(S.sc + 8), S.stepbar = reinterpret_cast<uint64_t*>(S.sc + 10);
+	S.steptab = reinterpret_cast<StepTab*>(S.sc + 16);
+	S.xch = smem_u32(S.steptab + max(P.T, 2));
+	S.sb = smem_u32(S.rows) + 4 * CPT * tid;
+	S.phase = 0, S.step_phase = 0;
+	if (tid == 0) { mbar_init(S.bar, 1); mbar_init(S.stepbar, blockDim.x >> 5); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+}
+
+/* One work item: tile `tile` of the block in flight of pair `slot` -- load, Tb fused next+extend steps, store.  On return the
+ * bulk stores of the tile are committed (not yet complete); returns the number of tiles of the block. */
+template<int MODE, int CPT>
+__device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const int slot, const int tile, bool &wrote_alive)
+{
+	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
+	int32_t *rows = S.rows;
+	int *sc = S.sc;
+	uint64_t *bar = S.bar, *stepbar = S.stepbar;
+	StepTab *steptab = S.steptab;
+	const uint32_t xch = S.xch, sb = S.sb;
+	uint32_t &phase = S.phase, &step_phase = S.step_phase;
+	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
+	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
+	const bool no_left = tid == 0, no_right = tid == NT - 1;
+	TileCtl *ctl = P.ctl + slot;
+	const int pi = P.order[P.pair0 + slot];
+	const PairDesc pd = P.pairs[pi];
+	const int tl = pd.tl, ql = pd.ql, doff = tile_doff(P, tl), dfin = ql - tl;
+	/* (fields of TileCtl and the alive words are written by other SMs inside the persistent kernel: read from L2, never through L1) */
+	const int Tb = __ldcg(&ctl->Tb), s0 = __ldcg(&ctl->s), n_tiles = __ldcg(&ctl->n_tiles), cur = __ldcg(&ctl->cur);
+	const int total4 = __ldcg(&ctl->total4), A4 = __ldcg(&ctl->A4);
+	const int u0 = (int)((long long)tile * total4 / n_tiles), u1 = (int)((long long)(tile + 1) * total4 / n_tiles);
+	const int ustart = A4 + 4 * u0, ulen = 4 * (u1 - u0), idx0 = ustart - HL;
+	const bool left_edge = tile == 0, right_edge = tile == n_tiles - 1;
+	int wflo_c = __ldcg(&ctl->wflo), wfhi_c = __ldcg(&ctl->wfhi);
+	int32_t *st_in = P.state + ((size_t)slot * 2 + cur) * R * pitch;
+	int32_t *st_out = P.state + ((size_t)slot * 2 + (cur ^ 1)) * R * pitch;
+	/* ---- load the tile: R rows of W int32, one bulk copy per row ---- */
+	if (tid < 32) {
+		fence_async_smem();
+		if (tid == 0) mbar_expect_tx(bar, (uint32_t)(R * W * 4));
+		__syncwarp();
+		for (int r = tid; r < R; r += 32)
+			bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
+	}
+	if (tid < 3) sc[tid] = 0;
+	if (P.fast && tid < max(Tb, 2)) { /* step tid+1 of the block works on score s0 + tid + 1 */
+		const int s = s0 + tid + 1;
+		const int4 h = P.tabH[s % n], a = P.tabE1[s % d1], b2 = P.tabE2[s % d2];
+		StepTab e;
+		e.h = h, e.e = make_int4(a.x, b2.x, a.z, b2.z);
+		steptab[tid] = e;
+	}
+	SeqView sv;
+	const int code_bits = P.packed ? P.packed[pi] : 0;
+	if (code_bits == 2) /* two-bit codes, 16 per word */
+		sv.T = P.seqp + (pd.t_off >> 3), sv.Q = P.seqp + (pd.q_off >> 3), sv.s_idx = 4, sv.s_amt = 1, sv.s_adv = 1;
+	else if (code_bits == 4) /* four-bit codes, 8 per word */
+		sv.T = P.seqp + (pd.t_off >> 3), sv.Q = P.seqp + (pd.q_off >> 3), sv.s_idx = 3, sv.s_amt = 2, sv.s_adv = 2;
+	else sv.T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), sv.Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off), sv.s_idx = 2, sv.s_amt = 3, sv.s_adv = 3;
+	const int c = CPT * tid, d0 = idx0 + c - doff;
+	const bool useful = c >= HL && c < HL + ulen;
+	const bool special = left_edge || right_edge || (dfin >= idx0 - doff && dfin < idx0 - doff + W); /* flags matter */
+	uint8_t *tbp = 0; /* traceback bytes of this thread's diagonals at the block's first score (wf_tb_add, :33-44) */
+	long long tb_pitch = 0;
+	if (MODE == MODE_TB) tbp = P.arena + __ldcg(&ctl->row_base) + (idx0 + c), tb_pitch = __ldcg(&ctl->row_size);
+	int kmin[CPT], kspan[CPT];
+#pragma unroll
+	for (int j = 0; j < CPT; ++j) { /* H is on the matrix iff kmin <= H <= kmin + kspan (:402) */
+		const int d = d0 + j, lo = max(-1, -1 - d), hi = min(tl - 1, ql - 1 - d);
+		if (hi >= lo) kmin[j] = lo, kspan[j] = hi - lo;
+		else kmin[j] = 0x3fffffff, kspan[j] = 0;
+	}
+	const int wd_lo = d0 - CPT * lane, wd_hi = wd_lo + 32 * CPT - 1;
+	const int bnd = (s0 | 0xff) + 1; /* next band trim */
+	const int t_alive = bnd - n - s0; /* steps t > t_alive feed wf_stripe_shrink (:144-171) */
+	int alive_bits = 0;
+	int hs = s0 % n, e1s = s0 % d1, e2s = s0 % d2;
+	mbar_wait(bar, phase);
+	phase ^= 1;
+	__syncthreads();
+	const long long snap_off = __ldcg(&ctl->snap_off);
+	if (snap_off >= 0) { /* snapshot for the segmented traceback: the state at score s0, useful columns of every row */
+		if (tid < 32) {
+			int32_t *dst = P.snap_arena + snap_off + (ustart - A4);
+			const int rs = __ldcg(&ctl->snap_rowsize);
+			fence_async_smem();
+			for (int r = tid; r < R; r += 32) bulk_s2g(dst + (size_t)r * rs, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
+			bulk_commit();
+			bulk_wait_read();
+		}
+		__syncthreads();
+	}
+	/* ---- Tb fused next+extend steps ---- */
+	CellOut<CPT> o;
+	bool stepped = false;
+	if (!special && Tb > 0 && P.fast >= 2 && code_bits != 0 && P.pen.e1 == 2 && P.pen.e2 == 1) { /* interior tile, packed codes, default gap extensions */
+		Fast2Ctx<CPT> c;
+		const uint32_t rb = 4u * W, cb = (uint32_t)code_bits;
+		const int warp = tid >> 5;
+		c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
+		c.edge_lane = (lane == 0 && !no_left) || (lane == 31 && !no_right);
+		c.nbh = sb + (lane == 0 ? -4 : 4 * CPT);
+		c.xr = xch + 16u * (warp + 1) + (lane == 0 ? 0u : 8u);                    /* side 0: from lane 31 of the warp before; side 1: from lane 0 of the next */
+		c.xw = xch + (lane == 0 ? 16u * warp + 8u : 16u * (warp + 2));           /* lane 0 writes side 1 of the warp before, lane 31 side 0 of the next */
+		c.seqw = P.seqp2;
+		const uint32_t tbits = (uint32_t)(sv.T - P.seqp) << 5, qbits = (uint32_t)(sv.Q - P.seqp) << 5;
+		c.c1 = tbits + cb, c.tend = tbits + cb * (uint32_t)tl, c.dq0 = qbits - tbits + cb * (uint32_t)d0;
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) c.kend[j] = (int)cb * min(tl - 1, ql - 1 - (d0 + j)) + (int)c.c1;
+		c.d0 = d0;
+		if (code_bits == 2) alive_bits = tile_fast2_block<MODE, CPT, 1>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+		else alive_bits = tile_fast2_block<MODE, CPT, 2>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+		__syncthreads();
+		stepped = true;
+	}
+	if constexpr (CPT == 4) {
+		if (stepped) {
+		} else if (!special && Tb > 0 && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
+			FastCtx c;
+			const uint32_t rb = 4u * W;
+			c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
+			c.edge_lane = (lane == 0 && !no_left) || (lane == 31 && !no_right);
+			c.f1off = d1 * rb, c.f2off = d2 * rb; /* rows: H [n], E1 [d1], F1 [d1], E2 [d2], F2 [d2] */
+			c.nb = sb + (lane == 0 ? -4 : 16);
+			c.nb1 = c.nb + (lane == 0 ? 0u : c.f1off), c.nb2 = c.nb + (lane == 0 ? 0u : c.f2off);
+			c.bs1 = lane == 31 ? sb + 12 : sb + c.f1off, c.bs2 = lane == 31 ? sb + 12 : sb + c.f2off;
+			c.lcb = sv.s_amt, c.cb = 1u << sv.s_amt, c.cb2 = 2u << sv.s_amt, c.cb3 = 3u << sv.s_amt;
+			c.seqw = code_bits ? P.seqp : reinterpret_cast<const uint32_t*>(P.seq);
+			c.tbits = (uint32_t)(sv.T - c.seqw) << 5;
+			c.dq0 = ((uint32_t)(sv.Q - c.seqw) << 5) - c.tbits + ((uint32_t)d0 << sv.s_amt);
+			c.d0 = d0;
+			c.tl = tl, c.ql = ql, c.tlm1 = tl - 1, c.qlm1d0 = ql - 1 - d0;
+			const int e1 = P.pen.e1, e2 = P.pen.e2;
+			if (e1 == 2 && e2 == 1) alive_bits = tile_fast_block<MODE, 2, 1>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+			else if (e1 == 2) alive_bits = tile_fast_block<MODE, 2, 2>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+			else if (e2 == 1) alive_bits = tile_fast_block<MODE, 1, 1>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+			else alive_bits = tile_fast_block<MODE, 1, 2>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
+			__syncthreads();
+			stepped = true;
+		} else if (!special) { /* interior tile, throughput geometry: split-phase step barrier */
+			for (int t = 1; t <= Tb; ++t) {
+				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
+				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
+				tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, sv, t > 1 && P.pen.e2 == 1, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
+				if (t > 1) ++step_phase;
+				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
+				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
+				if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); }
+			}
+			__syncthreads();
+			stepped = true;
+		}
+	}
+	if (stepped) {
+	} else if (!special) {
+		for (int t = 1; t <= Tb; ++t) {
+			hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
+			const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
+			tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
+			if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
+			if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
+			__syncthreads();
+		}
+	} else {
+		for (int t = 1; t <= Tb; ++t) {
+			hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
+			const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
+			const int lo_t = left_edge ? max(wflo_c - 1, -tl) : -0x3fffffff;   /* :417-418 */
+			const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
+			const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
+			if (edge) {
+				const int myfl = tile_cells<MODE, true, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
+				if (myfl) atomicOr(&sc[t % 3], myfl);
+			} else tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
+			if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
+			if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
+			if (tid == 0) {
+				sc[(t + 1) % 3] = 0;
+				if (left_edge) ctl->lo_log[t - 1] = lo_t;
+				if (right_edge) ctl->hi_log[t - 1] = hi_t;
+			}
+			__syncthreads();
+			const int fl = sc[t % 3];
+			if (fl & FL_LO) wflo_c = lo_t;
+			if (fl & FL_HI) wfhi_c = hi_t;
+			if ((fl & FL_DONE) && tid == 0 && __ldcg(&ctl->done_t) == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
+		}
+	}
+	/* ---- store the useful columns of every row into the other state buffer ---- */
+	if (tid < 32) {
+		fence_async_smem();
+		for (int r = tid; r < R; r += 32)
+			bulk_s2g(st_out + (size_t)r * pitch + ustart, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
+		bulk_commit();
+	}
+	if (tid == 0) {
+		if (left_edge) ctl->fin_lo = wflo_c;
+		if (right_edge) ctl->fin_hi = wfhi_c;
+	}
+	wrote_alive = Tb > t_alive;
+	if (Tb > t_alive && useful) { /* alive words: tag = score of the coming trim | alive bit */
+		int32_t *ap = P.alive + (size_t)slot * pitch + idx0 + c;
+#pragma unroll
+		for (int j = 0; j < CPT; ++j) {
+			const int a = __ldcg(ap + j);
+			__stcg(ap + j, ((a & ~1) == bnd ? a : bnd) | (alive_bits >> j & 1));
+		}
+	}
+	return n_tiles;
+}
+
+/* shared memory: rows[R][W] int32 | ctl ints [16] (flags, item, mbarriers) | step table | exchange records */
 template<int MODE, int CPT>
 __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa_tile_kernel(const __grid_constant__ TParams P, int it)
 {
 	extern __shared__ __align__(128) int32_t smem_tile[];
-	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
-	int32_t *rows = smem_tile;
-	int *sc = rows + (size_t)R * W;                          /* [0..2] flags, [3] item */
-	uint64_t *bar = reinterpret_cast<uint64_t*>(sc + 8), *stepbar = reinterpret_cast<uint64_t*>(sc + 10);
-	StepTab *steptab = reinterpret_cast<StepTab*>(sc + 16); /* [max(T, 2)] row offsets of the steps of the block in flight */
-	const uint32_t xch = smem_u32(steptab + max(P.T, 2)); /* [2][TILE_MAX_WARPS + 2] records of 16 bytes: gap cells across warp boundaries */
-	const int tid = threadIdx.x, lane = tid & 31, NT = blockDim.x;
-	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
+	TileSmem S;
+	tile_smem_setup<CPT>(P, smem_tile, S);
+	const int tid = threadIdx.x;
 	const unsigned int n_items = P.cnt[it & 1].n_items;
-	const uint32_t sb = smem_u32(rows) + 4 * CPT * tid;
-	const bool no_left = tid == 0, no_right = tid == NT - 1;
-	if (tid == 0) { mbar_init(bar, 1); mbar_init(stepbar, NT >> 5); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-	uint32_t phase = 0, step_phase = 0;
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) sc[3] = (int)atomicAdd(&P.cnt[it & 1].next, 1u);
+		if (tid == 0) S.sc[3] = (int)atomicAdd(&P.cnt[it & 1].next, 1u);
 		__syncthreads();
-		const unsigned int item = (unsigned int)sc[3];
+		const unsigned int item = (unsigned int)S.sc[3];
 		if (item >= n_items) break;
 		const int2 it2 = P.items[item];
-		const int slot = it2.x, tile = it2.y;
-		TileCtl *ctl = P.ctl + slot;
-		const int pi = P.order[P.pair0 + slot];
-		const PairDesc pd = P.pairs[pi];
-		const int tl = pd.tl, ql = pd.ql, doff = tile_doff(P, tl), dfin = ql - tl;
-		const int Tb = ctl->Tb, s0 = ctl->s, n_tiles = ctl->n_tiles, cur = ctl->cur;
-		const int u0 = (int)((long long)tile * ctl->total4 / n_tiles), u1 = (int)((long long)(tile + 1) * ctl->total4 / n_tiles);
-		const int ustart = ctl->A4 + 4 * u0, ulen = 4 * (u1 - u0), idx0 = ustart - HL;
-		const bool left_edge = tile == 0, right_edge = tile == n_tiles - 1;
-		int wflo_c = ctl->wflo, wfhi_c = ctl->wfhi;
-		int32_t *st_in = P.state + ((size_t)slot * 2 + cur) * R * pitch;
-		int32_t *st_out = P.state + ((size_t)slot * 2 + (cur ^ 1)) * R * pitch;
-		/* ---- load the tile: R rows of W int32, one bulk copy per row ---- */
-		if (tid < 32) {
-			fence_async_smem();
-			if (tid == 0) mbar_expect_tx(bar, (uint32_t)(R * W * 4));
-			__syncwarp();
-			for (int r = tid; r < R; r += 32)
-				bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
-		}
-		if (tid < 3) sc[tid] = 0;
-		if (CPT == 4 && P.fast && tid < max(Tb, 2)) { /* step tid+1 of the block works on score s0 + tid + 1 */
-			const int s = s0 + tid + 1;
-			const int4 h = P.tabH[s % n], a = P.tabE1[s % d1], b2 = P.tabE2[s % d2];
-			StepTab e;
-			e.h = h, e.e = make_int4(a.x, b2.x, a.z, b2.z);
-			steptab[tid] = e;
-		}
-		SeqView sv;
-		const int code_bits = P.packed ? P.packed[pi] : 0;
-		if (code_bits == 2) /* two-bit codes, 16 per word */
-			sv.T = P.seqp + (pd.t_off >> 3), sv.Q = P.seqp + (pd.q_off >> 3), sv.s_idx = 4, sv.s_amt = 1, sv.s_adv = 1;
-		else if (code_bits == 4) /* four-bit codes, 8 per word */
-			sv.T = P.seqp + (pd.t_off >> 3), sv.Q = P.seqp + (pd.q_off >> 3), sv.s_idx = 3, sv.s_amt = 2, sv.s_adv = 2;
-		else sv.T = reinterpret_cast<const uint32_t*>(P.seq + pd.t_off), sv.Q = reinterpret_cast<const uint32_t*>(P.seq + pd.q_off), sv.s_idx = 2, sv.s_amt = 3, sv.s_adv = 3;
-		const int c = CPT * tid, d0 = idx0 + c - doff;
-		const bool useful = c >= HL && c < HL + ulen;
-		const bool special = left_edge || right_edge || (dfin >= idx0 - doff && dfin < idx0 - doff + W); /* flags matter */
-		uint8_t *tbp = 0; /* traceback bytes of this thread's diagonals at the block's first score (wf_tb_add, :33-44) */
-		long long tb_pitch = 0;
-		if (MODE == MODE_TB) tbp = P.arena + ctl->row_base + (idx0 + c), tb_pitch = ctl->row_size;
-		int kmin[CPT], kspan[CPT];
-#pragma unroll
-		for (int j = 0; j < CPT; ++j) { /* H is on the matrix iff kmin <= H <= kmin + kspan (:402) */
-			const int d = d0 + j, lo = max(-1, -1 - d), hi = min(tl - 1, ql - 1 - d);
-			if (hi >= lo) kmin[j] = lo, kspan[j] = hi - lo;
-			else kmin[j] = 0x3fffffff, kspan[j] = 0;
-		}
-		const int wd_lo = d0 - CPT * lane, wd_hi = wd_lo + 32 * CPT - 1;
-		const int bnd = (s0 | 0xff) + 1; /* next band trim */
-		const int t_alive = bnd - n - s0; /* steps t > t_alive feed wf_stripe_shrink (:144-171) */
-		int alive_bits = 0;
-		int hs = s0 % n, e1s = s0 % d1, e2s = s0 % d2;
-		mbar_wait(bar, phase);
-		phase ^= 1;
-		__syncthreads();
-		if (ctl->snap_off >= 0) { /* snapshot for the segmented traceback: the state at score s0, useful columns of every row */
-			if (tid < 32) {
-				int32_t *dst = P.snap_arena + ctl->snap_off + (ustart - ctl->A4);
-				const int rs = ctl->snap_rowsize;
-				fence_async_smem();
-				for (int r = tid; r < R; r += 32) bulk_s2g(dst + (size_t)r * rs, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
-				bulk_commit();
-				bulk_wait_read();
-			}
-			__syncthreads();
-		}
-		/* ---- Tb fused next+extend steps ---- */
-		CellOut<CPT> o;
-		bool stepped = false;
-		if constexpr (CPT == 4) {
-			if (!special && P.fast >= 2 && code_bits == 2 && P.pen.e1 == 2 && P.pen.e2 == 1) { /* interior tile, two-bit codes, default gap extensions */
-				Fast2Ctx c;
-				const uint32_t rb = 4u * W;
-				const int warp = tid >> 5;
-				c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
-				c.edge_lane = (lane == 0 && !no_left) || (lane == 31 && !no_right);
-				c.nbh = sb + (lane == 0 ? -4 : 16);
-				c.xr = xch + 16u * (warp + 1) + (lane == 0 ? 0u : 8u);                    /* side 0: from lane 31 of the warp before; side 1: from lane 0 of the next */
-				c.xw = xch + (lane == 0 ? 16u * warp + 8u : 16u * (warp + 2));           /* lane 0 writes side 1 of the warp before, lane 31 side 0 of the next */
-				c.seqw = P.seqp2;
-				const uint32_t tbits = (uint32_t)(sv.T - P.seqp) << 5, qbits = (uint32_t)(sv.Q - P.seqp) << 5;
-				c.c1 = tbits + 2u, c.tend = tbits + 2u * (uint32_t)tl, c.dq0 = qbits - tbits + 2u * (uint32_t)d0;
-#pragma unroll
-				for (int j = 0; j < 4; ++j) c.kend[j] = 2 * min(tl - 1, ql - 1 - (d0 + j)) + (int)c.c1;
-				c.d0 = d0;
-				alive_bits = tile_fast2_block<MODE>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-				__syncthreads();
-				stepped = true;
-			} else if (!special && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
-				FastCtx c;
-				const uint32_t rb = 4u * W;
-				c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
-				c.edge_lane = (lane == 0 && !no_left) || (lane == 31 && !no_right);
-				c.f1off = d1 * rb, c.f2off = d2 * rb; /* rows: H [n], E1 [d1], F1 [d1], E2 [d2], F2 [d2] */
-				c.nb = sb + (lane == 0 ? -4 : 16);
-				c.nb1 = c.nb + (lane == 0 ? 0u : c.f1off), c.nb2 = c.nb + (lane == 0 ? 0u : c.f2off);
-				c.bs1 = lane == 31 ? sb + 12 : sb + c.f1off, c.bs2 = lane == 31 ? sb + 12 : sb + c.f2off;
-				c.lcb = sv.s_amt, c.cb = 1u << sv.s_amt, c.cb2 = 2u << sv.s_amt, c.cb3 = 3u << sv.s_amt;
-				c.seqw = code_bits ? P.seqp : reinterpret_cast<const uint32_t*>(P.seq);
-				c.tbits = (uint32_t)(sv.T - c.seqw) << 5;
-				c.dq0 = ((uint32_t)(sv.Q - c.seqw) << 5) - c.tbits + ((uint32_t)d0 << sv.s_amt);
-				c.d0 = d0;
-				c.tl = tl, c.ql = ql, c.tlm1 = tl - 1, c.qlm1d0 = ql - 1 - d0;
-				const int e1 = P.pen.e1, e2 = P.pen.e2;
-				if (e1 == 2 && e2 == 1) alive_bits = tile_fast_block<MODE, 2, 1>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-				else if (e1 == 2) alive_bits = tile_fast_block<MODE, 2, 2>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-				else if (e2 == 1) alive_bits = tile_fast_block<MODE, 1, 1>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-				else alive_bits = tile_fast_block<MODE, 1, 2>(c, steptab, sv, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-				__syncthreads();
-				stepped = true;
-			} else if (!special) { /* interior tile, throughput geometry: split-phase step barrier */
-				for (int t = 1; t <= Tb; ++t) {
-					hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
-					const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-					tile_cells_overlap<MODE>(sb, qh, q1, q2, d0, kmin, kspan, sv, t > 1 && P.pen.e2 == 1, no_left, no_right, stepbar, t > 1, step_phase & 1, o);
-					if (t > 1) ++step_phase;
-					if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
-					if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
-					if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); }
-				}
-				__syncthreads();
-				stepped = true;
-			}
-		}
-		if (stepped) {
-		} else if (!special) {
-			for (int t = 1; t <= Tb; ++t) {
-				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
-				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-				tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, 0, 0, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
-				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
-				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
-				__syncthreads();
-			}
-		} else {
-			for (int t = 1; t <= Tb; ++t) {
-				hs = hs + 1 == n ? 0 : hs + 1, e1s = e1s + 1 == d1 ? 0 : e1s + 1, e2s = e2s + 1 == d2 ? 0 : e2s + 1;
-				const int4 qh = P.tabH[hs], q1 = P.tabE1[e1s], q2 = P.tabE2[e2s];
-				const int lo_t = left_edge ? max(wflo_c - 1, -tl) : -0x3fffffff;   /* :417-418 */
-				const int hi_t = right_edge ? min(wfhi_c + 1, ql) : 0x3fffffff;
-				const bool edge = wd_lo <= lo_t || wd_hi >= hi_t || (dfin >= wd_lo && dfin <= wd_hi);
-				if (edge) {
-					const int myfl = tile_cells<MODE, true, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
-					if (myfl) atomicOr(&sc[t % 3], myfl);
-				} else tile_cells<MODE, false, CPT>(sb, qh, q1, q2, d0, lo_t, hi_t, dfin, tl, kmin, kspan, sv, no_left, no_right, useful, o);
-				if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, o.tb); tbp += tb_pitch; }
-				if (t > t_alive) alive_bits |= alive_cells<CPT>(d0, tl, ql, o);
-				if (tid == 0) {
-					sc[(t + 1) % 3] = 0;
-					if (left_edge) ctl->lo_log[t - 1] = lo_t;
-					if (right_edge) ctl->hi_log[t - 1] = hi_t;
-				}
-				__syncthreads();
-				const int fl = sc[t % 3];
-				if (fl & FL_LO) wflo_c = lo_t;
-				if (fl & FL_HI) wfhi_c = hi_t;
-				if ((fl & FL_DONE) && tid == 0 && ctl->done_t == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
-			}
-		}
-		/* ---- store the useful columns of every row into the other state buffer ---- */
-		if (tid < 32) {
-			fence_async_smem();
-			for (int r = tid; r < R; r += 32)
-				bulk_s2g(st_out + (size_t)r * pitch + ustart, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
-			bulk_commit();
-		}
-		if (tid == 0) {
-			if (left_edge) ctl->fin_lo = wflo_c;
-			if (right_edge) ctl->fin_hi = wfhi_c;
-		}
-		if (Tb > t_alive && useful) { /* alive words: tag = score of the coming trim | alive bit */
-			int32_t *ap = P.alive + (size_t)slot * pitch + idx0 + c;
-#pragma unroll
-			for (int j = 0; j < CPT; ++j) {
-				const int a = ap[j];
-				ap[j] = ((a & ~1) == bnd ? a : bnd) | (alive_bits >> j & 1);
-			}
-		}
+		bool wrote_alive;
+		tile_item<MODE, CPT>(P, S, it2.x, it2.y, wrote_alive);
 		if (tid < 32) bulk_wait_read(); /* the rows may be overwritten by the next item's load */
 	}
 	if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* stores complete before the CTA retires */
 }
 
+/*
+ * The persistent form: ONE launch per pass (per tile geometry) instead of one plan + one tile launch per block of scores.
+ * CTAs take tickets from a queue; the item of a ticket is a tile of some pair's block in flight, a pair to plan, or "retire".
+ * The CTA that finishes the last tile of a block (a counter in the pair's TileCtl) runs the planner for that pair on the spot
+ * -- replay, trim, cut, publish the next block's tiles -- so pairs advance independently: no launch boundary, no tail in which
+ * most SMs wait for the last tiles of a launch, and a single pair pays one counter + one planner call per block instead of two
+ * launches.  Ordering: a tile's bulk stores are complete (wait_group 0) and fenced before its CTA counts it done; the planner
+ * publishes an item with a fence between payload and sequence word; the consumer fences after seeing the sequence word (which
+ * also drops the SM's L1 lines) and crosses to the async proxy before its bulk loads.
+ */
+template<int MODE, int CPT>
+__global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa_tile_persist_kernel(const __grid_constant__ TParams P)
+{
+	extern __shared__ __align__(128) int32_t smem_tile[];
+	TileSmem S;
+	tile_smem_setup<CPT>(P, smem_tile, S);
+	const int tid = threadIdx.x;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) {
+			const unsigned int ticket = atomicAdd(&P.pq->head, 1u), i = ticket & P.q_mask;
+			unsigned int ns = 32;
+			while (ld_volatile_u32(P.q_seq + i) != ticket + 1u) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
+			/* no acquire fence here: it would drop the L1 lines of all four CTAs of the SM (the sequence windows) on every item.
+			 * The payload load below is issued only after the sequence word has been seen, the producer released it after the
+			 * payload, and everything other SMs write inside this kernel is read past L1 (ld.cg, bulk copies). */
+			const int2 v = __ldcg(P.q_items + i);
+			S.sc[3] = v.x, S.sc[4] = v.y, S.sc[5] = 0;
+		}
+		__syncthreads();
+		const int slot = S.sc[3], tile = S.sc[4];
+		if (slot < 0) break;
+		bool plan = tile < 0;
+		if (!plan) {
+			asm volatile("fence.proxy.async;" ::: "memory"); /* the state rows were written through the async proxy of other SMs */
+			bool wrote_alive;
+			const int n_tiles = tile_item<MODE, CPT>(P, S, slot, tile, wrote_alive);
+			if (tid < 32) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); asm volatile("fence.proxy.async;" ::: "memory"); }
+			if (wrote_alive) __threadfence(); /* one block in eight: every thread has stored alive words */
+			__syncthreads();
+			if (tid == 0) { /* release: the rows, the band logs and (through the barrier) what the other threads stored */
+				int prev;
+				asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(prev) : "l"(&P.ctl[slot].tiles_done) : "memory");
+				S.sc[5] = prev == n_tiles - 1;
+			}
+			__syncthreads();
+			plan = S.sc[5] != 0;
+		}
+		if (plan) {
+			__syncthreads();
+			if (tid == 0) S.sc[6] = 0;
+			plan_pair<true>(P, slot, 0, S.sc + 6);
+			__syncthreads();
+			if (S.sc[6]) { /* nothing in flight any more: one retire item per CTA of the grid */
+				if (tid == 0) S.sc[7] = (int)atomicAdd(&P.pq->tail, gridDim.x);
+				__syncthreads();
+				for (unsigned int j = tid; j < gridDim.x; j += blockDim.x) q_publish(P, (unsigned int)S.sc[7] + j, -1, -1);
+			}
+		}
+	}
+}
+
+/* start of a persistent pass (or of its continuation in the other tile geometry): one plan item per running pair */
+__global__ void wfa_tile_persist_begin_kernel(const TParams P, int grid)
+{
+	__shared__ int n_run;
+	if (threadIdx.x == 0) n_run = 0;
+	__syncthreads();
+	for (int slot = threadIdx.x; slot < P.n_pairs; slot += blockDim.x)
+		if (P.ctl[slot].status == TS_RUN) q_publish(P, (unsigned int)atomicAdd(&n_run, 1), slot, -1);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		P.pq->head = 0, P.pq->tail = (unsigned int)(n_run ? n_run : grid), P.pq->n_inflight = n_run, P.pq->stop_req = 0, P.pq->switch_to = P.geom_id, P.pq->n_start = n_run, P.pq->n_cut = 0;
+		int tot = 0;
+		for (int slot = 0; slot < P.n_pairs; ++slot) if (P.ctl[slot].status == TS_RUN) tot += P.ctl[slot].n_tiles;
+		P.pq->total_tiles = tot;
+	}
+	if (n_run == 0) /* nothing to do: retire the grid at once */
+		for (int j = threadIdx.x; j < grid; j += blockDim.x) q_publish(P, (unsigned int)j, -1, -1);
+}
+
 typedef void (*tile_kernel_fn)(const TParams, int);
+typedef void (*tile_persist_fn)(const TParams);
 
 static tile_kernel_fn tile_kernel_for(bool tb, int cpt)
 {
 	if (tb) return cpt == 4 ? wfa_tile_kernel<MODE_TB, 4> : cpt == 2 ? wfa_tile_kernel<MODE_TB, 2> : wfa_tile_kernel<MODE_TB, 1>;
 	return cpt == 4 ? wfa_tile_kernel<MODE_SCORE, 4> : cpt == 2 ? wfa_tile_kernel<MODE_SCORE, 2> : wfa_tile_kernel<MODE_SCORE, 1>;
+}
+
+static tile_persist_fn tile_persist_for(bool tb, int cpt)
+{
+	if (tb) return cpt == 4 ? wfa_tile_persist_kernel<MODE_TB, 4> : cpt == 2 ? wfa_tile_persist_kernel<MODE_TB, 2> : wfa_tile_persist_kernel<MODE_TB, 1>;
+	return cpt == 4 ? wfa_tile_persist_kernel<MODE_SCORE, 4> : cpt == 2 ? wfa_tile_persist_kernel<MODE_SCORE, 2> : wfa_tile_persist_kernel<MODE_SCORE, 1>;
 }
 
 /*
@@ -1331,7 +1549,7 @@ __global__ void wfa_tile_segstart_kernel(const TParams P, int j)
 	}
 	if (blockIdx.y == 0 && threadIdx.x == 0) {
 		c->s = d.s, c->wflo = d.wflo, c->wfhi = d.wfhi, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = d.n_iter;
-		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1;
+		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1, c->tiles_done = 0;
 		c->status = TS_RUN;
 		atomicAdd(P.n_running, 1);
 		P.s_stop[slot] = j == n_snap ? ts->s_final : (j + 1) * P.snap_P;

@@ -11,6 +11,7 @@ time on this container's CPU (one thread), which is NOT the box of the bench -- 
 import hashlib
 import json
 import os
+import re
 import struct
 import sys
 import time
@@ -89,7 +90,10 @@ def main():
         c = run_config3() if name == "config3" else run_case(name)
         doc["cases"] = [x for x in doc["cases"] if x["name"] != name] + [c]
         with open(OUT + ".tmp", "w") as f:
-            json.dump(doc, f, indent=1)
+            txt = json.dumps(doc, indent=1)  # the 1024 (s, n_iter) rows of config 3 on one line
+            txt = re.sub(r'"s_n_iter": \[(?:.|\n)*?\]\s*\]',
+                         lambda m: '"s_n_iter": ' + json.dumps(json.loads(m.group(0)[len('"s_n_iter": '):]), separators=(",", ":")), txt)
+            f.write(txt + "\n")
         os.replace(OUT + ".tmp", OUT)
         e = c["expect"]
         print(name, {k: v for k, v in e.items() if k != "s_n_iter"}, c["reference_seconds_here"], "s", flush=True)
