@@ -448,7 +448,7 @@ def main():
                 bb.run()
                 rr = bb.fetch()
                 if world > 1:  # the one collective of the path: mwf_rst_t records of every shard -> rank 0
-                    mdist.gather_to_root(list(range(first, first + P)), rr, P * world)
+                    mdist.gather_to_root(list(range(first, first + P)), rr, P * world, fixed=True)  # score-only: one gather of equal-sized records
                 return rr, bb.h2d_bytes, bb.d2h_bytes
 
         for _ in range(min(warmup, 2)):

@@ -55,6 +55,11 @@ int  mwf_b200_device_count(void);
 /* device used by batches created afterwards on any thread; default: $MWF_B200_DEVICE, else $LOCAL_RANK, else 0 */
 void mwf_b200_set_device(int dev);
 int  mwf_b200_get_device(void);
+/* devices one mwf_wfa_exact_batch() call is spread over: 1 = the current device only; n > 1 = n devices starting at the current
+ * one; 0 (default) = every visible device ($MWF_B200_DEVICES caps them) unless a device was pinned by mwf_b200_set_device(),
+ * $MWF_B200_DEVICE or $LOCAL_RANK (one process per GPU), and only for batches worth it (sum of squared lengths >= 1e11).  Pairs are
+ * dealt out by cost; no data moves between devices. */
+void mwf_b200_set_devices(int n);
 /* force a kernel family (tests/bench); default: $MWF_B200_KERNEL ("cta"/"grid"/"tile"), else AUTO */
 void mwf_b200_set_kernel(int kernel);
 /* device and pinned-host workspaces are cached across batches; this frees every cached buffer */
@@ -66,9 +71,9 @@ mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t n_pairs, c
 /* run on this CUDA stream (a cudaStream_t) instead of the batch's own */
 void mwf_b200_batch_set_stream(mwf_b200_batch_t *b, void *cuda_stream);
 void mwf_b200_batch_upload(mwf_b200_batch_t *b, const char *const *ts, const char *const *qs); /* host -> pinned -> HBM, async */
-void mwf_b200_batch_run(mwf_b200_batch_t *b);     /* run the alignment kernels; returns once every launch is enqueued (the tile engine's
-                                                      host loop launches one plan + one tile kernel per block of scores and reads the
-                                                      number of running pairs back one chunk behind, so it returns near the end) */
+void mwf_b200_batch_run(mwf_b200_batch_t *b);     /* run the alignment kernels on the batch's stream.  The tile engine runs a pass as one
+                                                      persistent kernel and reads its outcome back, so this returns when the batch is
+                                                      (nearly) done; the streaming kernels are only enqueued */
 void mwf_b200_batch_wait(mwf_b200_batch_t *b);    /* block until the stream is idle; aborts on a device-side error */
 void mwf_b200_batch_fetch(mwf_b200_batch_t *b, void *km, mwf_rst_t *r); /* HBM -> host; r[0..n_pairs) */
 void mwf_b200_batch_destroy(mwf_b200_batch_t *b);

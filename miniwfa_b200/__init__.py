@@ -7,10 +7,10 @@ There is no CPU implementation here; loading fails loudly if the library is miss
 """
 from .api import (MwfOpt, MwfRst, Batch, opt_init, wfa_exact, wfa_auto, wfa_chain, wfa_exact_batch,
                   kmer_hits, kmer_shared,
-                  cigar_string, cigar2score, device_count, set_device, set_kernel, release_cache, lib,
+                  cigar_string, cigar2score, device_count, set_device, set_devices, set_kernel, release_cache, lib,
                   F_CIGAR, F_NO_KALLOC, KERNEL_AUTO, KERNEL_CTA, KERNEL_GRID, KERNEL_TILE)
 from . import synth
 
 __all__ = ["MwfOpt", "MwfRst", "Batch", "opt_init", "wfa_exact", "wfa_auto", "wfa_exact_batch", "wfa_chain", "kmer_hits", "kmer_shared",
-           "cigar_string", "cigar2score", "device_count", "set_device", "set_kernel", "release_cache", "lib", "synth",
+           "cigar_string", "cigar2score", "device_count", "set_device", "set_devices", "set_kernel", "release_cache", "lib", "synth",
            "F_CIGAR", "F_NO_KALLOC", "KERNEL_AUTO", "KERNEL_CTA", "KERNEL_GRID", "KERNEL_TILE"]

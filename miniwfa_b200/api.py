@@ -6,6 +6,8 @@ which runs the CUDA kernels.  If the library is absent this module raises at fir
 import ctypes
 import os
 
+import numpy as _np
+
 F_CIGAR = 0x1
 F_NO_KALLOC = 0x2
 KERNEL_AUTO, KERNEL_CTA, KERNEL_GRID, KERNEL_TILE = 0, 1, 2, 3
@@ -100,6 +102,11 @@ def set_device(dev):
     lib().mwf_b200_set_device(int(dev))
 
 
+def set_devices(n):
+    """mwf_b200_set_devices(): devices one mwf_wfa_exact_batch() call is spread over (0 = automatic, 1 = the current one)."""
+    lib().mwf_b200_set_devices(int(n))
+
+
 def set_kernel(kernel):
     lib().mwf_b200_set_kernel(int(kernel))
 
@@ -111,7 +118,7 @@ def release_cache():
 
 def _take(r, km=None):
     """Copy a result out of an mwf_rst_t and release its CIGAR (allocated from km / malloc)."""
-    cig = [r.cigar[i] for i in range(r.n_cigar)] if r.n_cigar > 0 else []
+    cig = _np.ctypeslib.as_array(r.cigar, shape=(r.n_cigar,)).tolist() if r.n_cigar > 0 else []  # one C loop, not one ctypes call per word
     if r.cigar:
         lib().kfree(km, r.cigar)
     return (r.s, r.n_cigar, r.n_iter, cig)

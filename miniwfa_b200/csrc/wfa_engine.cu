@@ -39,6 +39,7 @@
 #include <vector>
 #include <atomic>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include "mwf_b200.h"
 #include "kalloc.h"
@@ -752,6 +753,8 @@ __global__ void __launch_bounds__(512, 1) wfa_grid_kernel(const KParams P)
 /* ------------------------------------------------------------------------------------------ */
 
 static std::atomic<int> g_device(-1), g_kernel(-1), g_threads(0);
+static std::atomic<int> g_device_explicit(0), g_n_devices(0);
+static thread_local int tl_device = -1; /* set by the per-device workers of mwf_wfa_exact_batch: the device of batches this thread creates */
 
 static int env_int(const char *name, int dflt)
 {
@@ -766,7 +769,8 @@ extern "C" int mwf_b200_device_count(void)
 	return n;
 }
 
-extern "C" void mwf_b200_set_device(int dev) { g_device = dev; }
+extern "C" void mwf_b200_set_device(int dev) { g_device = dev; g_device_explicit = 1; }
+extern "C" void mwf_b200_set_devices(int n) { g_n_devices = n < 0 ? 0 : n; }
 
 extern "C" int mwf_b200_get_device(void)
 {
@@ -1087,7 +1091,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	if (opt->x <= 0 || opt->e1 <= 0 || opt->e2 <= 0 || opt->o1 < 0 || opt->o2 < 0)
 		die("penalties must satisfy x>0, e1>0, e2>0, o1>=0, o2>=0");
 	mwf_b200_batch_t *b = new mwf_b200_batch_t();
-	b->dev = mwf_b200_get_device();
+	b->dev = tl_device >= 0 ? tl_device : mwf_b200_get_device();
 	CUDA_OK(cudaSetDevice(b->dev));
 	int smem_optin = 0; /* (cudaGetDeviceProperties costs tens of milliseconds; two attributes are all that is needed) */
 	CUDA_OK(cudaDeviceGetAttribute(&b->n_sm, cudaDevAttrMultiProcessorCount, b->dev));
@@ -1798,9 +1802,28 @@ extern "C" int mwf_b200_batch_kernel_used(const mwf_b200_batch_t *b) { return b-
 extern "C" int64_t mwf_b200_batch_h2d_bytes(const mwf_b200_batch_t *b) { return b->h2d; }
 extern "C" int64_t mwf_b200_batch_d2h_bytes(const mwf_b200_batch_t *b) { return b->d2h; }
 
-extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pairs,
-                                    const int32_t *tl, const char *const *ts,
-                                    const int32_t *ql, const char *const *qs, mwf_rst_t *r)
+/* How many devices a batch is spread over.  mwf_b200_set_devices(n): n = 1 keeps every batch on one device, n > 1 uses n
+ * devices starting at the current one, 0 (default) decides per batch: all visible devices ($MWF_B200_DEVICES caps them) when
+ * no device was pinned -- by mwf_b200_set_device(), $MWF_B200_DEVICE or $LOCAL_RANK (one process per GPU: torchrun, MPI) --
+ * and the batch is worth it (at least two pairs and a sum of squared lengths of 1e11 -- ten 100 kb pairs: a device costs
+ * about a millisecond to set up, and the many tiny gap fills of mwf_wfa_chain must stay on one). */
+static int batch_devices(int n_pairs, const int32_t *tl, const int32_t *ql)
+{
+	int want = g_n_devices;
+	if (want == 1 || n_pairs < 2) return 1;
+	const int vis = mwf_b200_device_count();
+	if (want == 0) {
+		if (g_device_explicit || getenv("MWF_B200_DEVICE") || getenv("LOCAL_RANK")) return 1;
+		want = env_int("MWF_B200_DEVICES", vis);
+		double work = 0; /* wavefront cells grow with the square of the length */
+		for (int i = 0; i < n_pairs; ++i) work += (double)std::max(tl[i], ql[i]) * std::max(tl[i], ql[i]);
+		if (work < 1e11) return 1;
+	}
+	return std::max(1, std::min(std::min(want, vis), n_pairs));
+}
+
+static void exact_batch_one_device(void *km, const mwf_opt_t *opt, int32_t n_pairs, const int32_t *tl, const char *const *ts,
+                                   const int32_t *ql, const char *const *qs, mwf_rst_t *r)
 {
 	const bool timing = getenv("MWF_B200_BATCH_TIMING") != 0; /* phase times to stderr */
 	double t[6] = { 0, 0, 0, 0, 0, 0 };
@@ -1822,6 +1845,60 @@ extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pa
 	if (timing)
 		fprintf(stderr, "[mwf_b200] batch of %d: create %.2f, upload %.2f, run %.2f, fetch %.2f, destroy %.2f ms\n", n_pairs,
 		        t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]);
+}
+
+/* n independent pairs (the reference's CLI loops over them, main.c:67).  With several devices the pairs are dealt
+ * out by cost (wavefront cells grow with the square of the length; longest first, each to the least loaded device), one host
+ * thread per device creates, uploads and runs its shard on its own stream, and the calling thread then fetches shard after
+ * shard: the results -- CIGARs from the caller's km, which is not thread-safe -- land in r in input order.  No data crosses
+ * between devices. */
+extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pairs,
+                                    const int32_t *tl, const char *const *ts,
+                                    const int32_t *ql, const char *const *qs, mwf_rst_t *r)
+{
+	const int n_dev = batch_devices(n_pairs, tl, ql);
+	if (n_dev <= 1) { exact_batch_one_device(km, opt, n_pairs, tl, ts, ql, qs, r); return; }
+	const int dev0 = mwf_b200_get_device(), vis = mwf_b200_device_count();
+	struct Shard { std::vector<int> idx; std::vector<int32_t> tl, ql; std::vector<const char*> ts, qs; std::vector<mwf_rst_t> r; mwf_b200_batch_t *b; double load; };
+	std::vector<Shard> sh(n_dev);
+	for (int d = 0; d < n_dev; ++d) sh[d].b = 0, sh[d].load = 0;
+	std::vector<int> order(n_pairs);
+	for (int i = 0; i < n_pairs; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return std::max(tl[a], ql[a]) > std::max(tl[c], ql[c]); });
+	for (int k = 0; k < n_pairs; ++k) {
+		const int i = order[k];
+		int best = 0;
+		for (int d = 1; d < n_dev; ++d) if (sh[d].load < sh[best].load) best = d;
+		const double n = std::max(tl[i], ql[i]);
+		sh[best].load += n * n + 1.0;
+		sh[best].idx.push_back(i);
+	}
+	std::vector<std::thread> workers;
+	for (int d = 0; d < n_dev; ++d) {
+		Shard &S = sh[d];
+		std::sort(S.idx.begin(), S.idx.end());
+		for (size_t k = 0; k < S.idx.size(); ++k) {
+			const int i = S.idx[k];
+			S.tl.push_back(tl[i]), S.ql.push_back(ql[i]), S.ts.push_back(ts[i]), S.qs.push_back(qs[i]);
+		}
+		S.r.resize(S.idx.size());
+		workers.push_back(std::thread([&S, d, dev0, vis, opt]() {
+			tl_device = (dev0 + d) % vis;
+			S.b = mwf_b200_batch_create(opt, (int32_t)S.idx.size(), S.tl.data(), S.ql.data());
+			mwf_b200_batch_upload(S.b, S.ts.data(), S.qs.data());
+			mwf_b200_batch_run(S.b);
+			mwf_b200_batch_wait(S.b);
+			tl_device = -1;
+		}));
+	}
+	for (size_t d = 0; d < workers.size(); ++d) workers[d].join();
+	for (int d = 0; d < n_dev; ++d) {
+		Shard &S = sh[d];
+		mwf_b200_batch_fetch(S.b, km, S.r.data());
+		for (size_t k = 0; k < S.idx.size(); ++k) r[S.idx[k]] = S.r[k];
+		mwf_b200_batch_destroy(S.b);
+	}
+	CUDA_OK(cudaSetDevice(dev0));
 }
 
 #include "kmer_front.cuh"

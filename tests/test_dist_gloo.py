@@ -42,6 +42,11 @@ def _worker(rank, world, port, balance, q):
                 assert got == want, kw
             else:
                 assert got is None
+        # score-only batches: the results travel in ONE collective (a gather of equal-sized records)
+        idx = mdist.shard_indices(len(pairs), world, rank)
+        local = _oracle_align(orc.make_opt(), [pairs[i] for i in idx])
+        got = mdist.gather_to_root(idx, local, len(pairs), fixed=True)
+        assert (got == _oracle_align(orc.make_opt(), pairs)) if rank == 0 else got is None
         # an empty batch and a batch smaller than the world
         assert mdist.wfa_exact_batch_sharded(orc.make_opt(), [], align_fn=_oracle_align) in ([], None)
         one = mdist.wfa_exact_batch_sharded(orc.make_opt(flag=1), pairs[2:3], align_fn=_oracle_align)

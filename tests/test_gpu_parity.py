@@ -609,3 +609,23 @@ def test_reference_cli_linked_against_this_library(tmp_path):
         out = subprocess.run([exe] + ([flags] if flags else []) + [str(f1), str(f2)], capture_output=True, text=True, timeout=120)
         assert out.returncode == 0, out.stderr
         assert out.stdout.strip() == head + tail, (flags, out.stdout)
+
+
+def test_batch_spread_over_devices():
+    """mwf_wfa_exact_batch() through the C ABI with the pairs dealt out over two devices by one host process: the
+    results, CIGARs from the caller's allocator included, in input order and equal to the one-device call."""
+    if mw.device_count() < 2:
+        pytest.skip("needs two visible devices (gpurun --gpus 2)")
+    mw.set_kernel(mw.KERNEL_AUTO)
+    pairs = synth.make_batch(6, 30000, 0.05, 500) + synth.make_batch(5, 12000, 0.1, 600) + [(b"ACGT", b"ACGA"), (b"", b"A")]
+    for kw in ({}, {"flag": mw.F_CIGAR}, {"flag": mw.F_CIGAR, "step": 2000}):
+        mw.set_devices(1)
+        one = mw.wfa_exact_batch(mw.opt_init(**kw), pairs)
+        mw.set_devices(2)
+        try:
+            two = mw.wfa_exact_batch(mw.opt_init(**kw), pairs)
+        finally:
+            mw.set_devices(0)
+        assert two == one, kw
+    t, q = pairs[0]
+    assert one[0] == orc.checker_exact(orc.make_opt(flag=1, step=2000), t, q)
