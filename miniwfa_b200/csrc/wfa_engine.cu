@@ -835,6 +835,8 @@ static size_t ws_cached_bytes(int dev)
 	return t;
 }
 
+static thread_local bool g_ws_soft = false; /* ws_alloc reports an exhausted device instead of aborting (ws_dev_shrinking) */
+
 /* returns true when the memory is fresh (never used by an earlier batch) */
 static bool ws_alloc(void **out, size_t bytes, bool host, int dev)
 {
@@ -862,6 +864,7 @@ static bool ws_alloc(void **out, size_t bytes, bool host, int dev)
 		mwf_b200_release_cache();
 		err = host ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
 	}
+	if (err == cudaErrorMemoryAllocation && g_ws_soft) { cudaGetLastError(); *out = 0; return false; }
 	CUDA_OK(err);
 	WsEntry e = { p, bytes, dev, host };
 	std::lock_guard<std::mutex> lk(g_ws_mu);
@@ -915,6 +918,23 @@ static void ws_free(void *p)
 }
 
 template<class T> static bool ws_dev(T **out, size_t bytes, int dev) { return ws_alloc((void**)out, bytes, false, dev); }
+
+/* The traceback arena is sized from the memory that is free at that moment; another thread or another allocator of the process
+ * may take some of it before the cudaMalloc.  Rather than aborting, ask for less: every mode works with a smaller arena (the
+ * batch then goes through waves, a rerun with the grown arena, or the segmented traceback).  Returns the bytes obtained. */
+static long long ws_dev_shrinking(uint8_t **out, long long want, long long floor_bytes, int dev)
+{
+	for (long long bytes = want; bytes >= floor_bytes; bytes = (bytes / 2) & ~255LL) {
+		g_ws_soft = true;
+		ws_alloc((void**)out, (size_t)bytes, false, dev);
+		g_ws_soft = false;
+		if (*out) return bytes;
+		fprintf(stderr, "[mwf_b200] %lld bytes of device memory for the traceback arena are not available (another allocator took them): trying half\n", bytes);
+	}
+	fprintf(stderr, "[mwf_b200] not enough free device memory for the traceback arena\n");
+	abort();
+	return 0;
+}
 template<class T> static bool ws_host(T **out, size_t bytes) { return ws_alloc((void**)out, bytes, true, 0); }
 
 /* an "as much as is free" buffer (the traceback arena when the worst case exceeds the budget): any cached device buffer of at
@@ -992,6 +1012,8 @@ struct mwf_b200_batch {
 	unsigned int *d_qseq;
 	unsigned int q_mask;
 	bool persist;
+	double s_est;          /* a high estimate of the largest score of the batch (shared 13-mers), 0 when unknown */
+	bool arena_deferred;   /* a few very long pairs: the traceback arena is sized in mwf_b200_batch_run, from the pairs' shared 13-mers */
 	unsigned char *d_tmisc; /* TileCounters[2] @0, n_running @32, arena_used @64 */
 	int *h_running;
 	cudaEvent_t evc[2];
@@ -1200,7 +1222,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	ws_dev(&b->d_order, sizeof(int) * std::max(1, n_pairs), b->dev);
 	ws_dev(&b->d_ctl, 64, b->dev);
 	b->d_ring = 0, b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
-	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->q_mask = 0, b->persist = false, b->d_tmisc = 0, b->h_running = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->q_mask = 0, b->persist = false, b->arena_deferred = false, b->s_est = 0, b->d_tmisc = 0, b->h_running = 0;
 	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0, b->wave_pairs = 0;
 	if (b->is_tb) ws_dev(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw), b->dev);
 	if (pref == MWF_B200_KERNEL_TILE) {
@@ -1266,7 +1288,14 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			if (env_int("MWF_B200_TILE_ARENA_MAX", 0) > 0) /* tests */
 				b->arena_total = b->arena_full = std::min<long long>(b->arena_total, env_int("MWF_B200_TILE_ARENA_MAX", 0));
 			if (b->arena_total < 4096) die("not enough free device memory for the traceback arena");
-			ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
+			/* a few very long pairs whose expected arena is everything that is free: wait for the sequences (mwf_b200_batch_run
+			 * estimates the score from the shared 13-mers, 3 ms) instead of taking ~150 GB that the run may never touch */
+			b->arena_deferred = b->arena_total >= b->arena_full && env_int("MWF_B200_TILE_PREDICT", 1) && n_pairs <= 8 &&
+			                    max_len >= env_int("MWF_B200_TILE_PREDICT_MINLEN", 2000000) && !env_int("MWF_B200_TILE_ARENA_MAX", 0);
+			if (!b->arena_deferred) {
+				b->arena_total = ws_dev_shrinking(&b->d_arena, b->arena_total, 4096, b->dev);
+				b->arena_full = std::max(b->arena_full, b->arena_total);
+			}
 		}
 		for (int g = 0; g < b->n_geom; ++g) {
 			mwf_b200_batch::TileGeom &G = b->geom[g];
@@ -1530,9 +1559,9 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		CUDA_OK(cudaStreamSynchronize(b->stream));
 		ws_free(b->d_arena);
 		b->d_arena = 0;
-		mwf_b200_release_cache();
 		size_t free_b = 0, total_b = 0;
 		CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+		free_b += ws_cached_bytes(b->dev); /* (cached buffers count as free: ws_alloc hands them out, or releases them when it must) */
 		b->seg_P = std::max(256, env_int("MWF_B200_TILE_SEGP", 4096) & ~255);
 		b->snapdir_stride = (int)(b->max_sbound / b->seg_P + 2);
 		const long long half = (long long)((double)free_b * 0.45) & ~255LL;
@@ -1541,7 +1570,16 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		if (lowmem) need = half; /* ... and of pass 2, which is banded only while the reference's checkpoint matching keeps up: with
 		                            step below the penalties two snapshots can share a checkpoint and the band stops collapsing (:413-416) */
 		b->arena_total = std::min(half, (need + 255) & ~255LL);
-		b->snap_words = std::min(half, (long long)b->snapdir_stride * b->tR * width * 4 * wp) / 4;
+		/* snapshots: R rows as wide as the band, one every seg_P scores.  Worst case: the all-gap score bound at full width; with
+		 * a score estimate (a few very long pairs): the band of snapshot k is ~ 2 k seg_P wide.  Too small an estimate is found
+		 * out by the forward pass, which is then rerun with the worst case. */
+		long long snap_bytes = std::min(half, (long long)b->snapdir_stride * b->tR * width * 4 * wp);
+		if (b->s_est > 0) {
+			const double n_snap = b->s_est / b->seg_P + 2, w0 = 2.0 * b->pen.nring + 2.0 * TILE_TMAX + 64;
+			const double est = 1.25 * wp * b->tR * 4.0 * (b->seg_P * n_snap * n_snap + n_snap * w0) + (64 << 20);
+			snap_bytes = std::min(snap_bytes, (long long)est & ~255LL);
+		}
+		b->snap_words = snap_bytes / 4;
 		ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		ws_dev(&b->d_snap, (size_t)b->snap_words * 4, b->dev);
 		ws_dev(&b->d_snapdir, sizeof(SnapDir) * (size_t)b->snapdir_stride * wp, b->dev);
@@ -1566,7 +1604,22 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 			PP[g].seg_use = 0;
 		}
 		CUDA_OK(cudaMemsetAsync(b->d_nsnap, 0, sizeof(int) * np, b->stream));
-		if (tile_pass(b, PP, np, -1, true)) die("device workspace exhausted (snapshots of the segmented traceback)");
+		const bool timing = getenv("MWF_B200_BATCH_TIMING") != 0;
+		struct timespec tsx;
+		double t_fwd = 0, t_pass = 0, t_walk = 0, t0x = 0, t1x = 0;
+#define SEG_NOW(v_) do { if (timing) { CUDA_OK(cudaStreamSynchronize(b->stream)); clock_gettime(CLOCK_MONOTONIC, &tsx); v_ = 1e3 * tsx.tv_sec + 1e-6 * tsx.tv_nsec; } } while (0)
+		SEG_NOW(t0x);
+		if (tile_pass(b, PP, np, -1, true)) {
+			if (b->s_est <= 0) die("device workspace exhausted (snapshots of the segmented traceback)");
+			/* the score estimate was too low: the worst-case snapshot arena, and once more from score 0 */
+			b->s_est = 0;
+			CUDA_OK(cudaStreamSynchronize(b->stream));
+			ws_free(b->d_snap); ws_free(b->d_snapdir); ws_free(b->d_nsnap); ws_free(b->d_sstop); ws_free(b->d_trace); ws_free(b->h_nsnap);
+			b->d_snap = 0, b->d_snapdir = 0, b->d_nsnap = 0, b->d_sstop = 0, b->d_trace = 0, b->h_nsnap = 0;
+			run_tile_segmented(b);
+			return;
+		}
+		SEG_NOW(t1x); t_fwd = t1x - t0x;
 		wfa_tile_trace_begin_kernel<<<(np + 127) / 128, 128, 0, b->stream>>>(PP[0]);
 		CUDA_OK(cudaGetLastError());
 		++b->launches;
@@ -1582,12 +1635,17 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		for (int g = 0; g < 2; ++g)
 			PP[g].is_tb = 1, PP[g].snap_take = 0, PP[g].s_stop = b->d_sstop, PP[g].max_s = 0, PP[g].max_iter = 0;
 		for (int j = max_seg; j >= 0; --j) {
+			SEG_NOW(t0x);
 			if (tile_pass(b, PP, np, j, false)) die("device workspace exhausted (traceback bytes of one segment); lower MWF_B200_TILE_SEGP");
+			SEG_NOW(t1x); t_pass += t1x - t0x;
 			if (lowmem) wfa_tile_ckpt_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
 			else wfa_tile_trace_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
 			CUDA_OK(cudaGetLastError());
 			++b->launches;
+			SEG_NOW(t0x); t_walk += t0x - t1x;
 		}
+		if (timing) fprintf(stderr, "[mwf_b200] segmented traceback: forward pass with snapshots %.1f ms, %d segments recomputed %.1f ms, walked %.1f ms\n", t_fwd, max_seg + 1, t_pass, t_walk);
+#undef SEG_NOW
 		if (lowmem && env_int("MWF_B200_DEBUG", 0)) {
 			int ns = 0, sg[16];
 			CUDA_OK(cudaStreamSynchronize(b->stream));
@@ -1623,10 +1681,11 @@ static bool grow_arena(mwf_b200_batch_t *b)
  * beforehand (3 ms, kmer_front.cuh): f ~ (1 - p)^13 for a per-base difference rate p, s >~ 0.8 x p n (every difference costs
  * at least about a mismatch; 0.8 leaves room for the estimate), and the bytes are ~ s^2.  A wrong guess only costs time -- both
  * routes give the same CIGAR -- so the test is one-sided: skip the attempt only when the low estimate already overflows. */
-static bool predict_arena_overflow(const mwf_b200_batch_t *b)
+static bool predict_arena_overflow(mwf_b200_batch_t *b, double *bytes_likely = 0)
 {
+	if (bytes_likely) *bytes_likely = 0;
 	if (!env_int("MWF_B200_TILE_PREDICT", 1) || b->n > 8 || b->max_len < env_int("MWF_B200_TILE_PREDICT_MINLEN", 2000000)) return false;
-	double bytes = 0;
+	double bytes = 0, likely = 0;
 	for (int i = 0; i < b->n; ++i) {
 		const PairDesc &p = b->pairs[i];
 		int64_t n1 = 0, n2 = 0, shared = 0;
@@ -1634,10 +1693,31 @@ static bool predict_arena_overflow(const mwf_b200_batch_t *b)
 		mwf_b200_kmer_shared(p.tl, (const char*)b->h_seq + p.t_off, p.ql, (const char*)b->h_seq + p.q_off, 13, &n1, &n2, &shared);
 		const double f = std::min(n1, n2) > 0 ? (double)shared / (double)std::min(n1, n2) : 0.0;
 		const double diff = 1.0 - pow(std::min(1.0, std::max(f, 1e-9)), 1.0 / 13.0);
-		const double s_low = 0.8 * b->opt.x * diff * std::max(p.tl, p.ql) + gap_cost(&b->opt, p.tl > p.ql ? p.tl - p.ql : p.ql - p.tl);
+		const double gap = gap_cost(&b->opt, p.tl > p.ql ? p.tl - p.ql : p.ql - p.tl), xn = b->opt.x * diff * std::max(p.tl, p.ql);
+		const double s_low = 0.8 * xn + gap, s_hi = 1.35 * xn + gap + 4096; /* (synthetic 5 Mb pairs: s = 1.19 x n diff) */
 		bytes += s_low * s_low;
+		likely += s_hi * s_hi + (TILE_TMAX + 2.0) * ((double)p.tl + p.ql);
+		b->s_est = std::max(b->s_est, s_hi);
 	}
+	if (bytes_likely) *bytes_likely = likely;
 	return bytes > (double)b->arena_full;
+}
+
+/* the deferred arena of a few very long pairs: what the pairs are likely to need (a low guess only costs a rerun with the grown
+ * arena), or nothing at all when even the low estimate overflows the device -- the segmented traceback brings its own */
+static bool size_deferred_arena(mwf_b200_batch_t *b)
+{
+	double likely = 0;
+	const bool overflow = predict_arena_overflow(b, &likely);
+	b->arena_deferred = false;
+	if (overflow) return true;
+	size_t free_b = 0, total_b = 0;
+	CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+	free_b += ws_cached_bytes(b->dev);
+	b->arena_full = std::min(b->arena_full, (long long)((double)free_b * env_int("MWF_B200_ARENA_PCT", 85) / 100.0) & ~255LL);
+	const long long want = (long long)std::min((double)b->arena_full, std::max(likely, 64.0 * 1048576)) & ~255LL;
+	b->arena_total = ws_dev_shrinking(&b->d_arena, want, 4096, b->dev);
+	return false;
 }
 
 extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
@@ -1648,7 +1728,8 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 	if (b->n > 0) {
 		if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb && b->opt.step <= 0) { /* high-memory CIGAR */
 			bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
-			if (!segmented && b->arena_total >= b->arena_full && predict_arena_overflow(b)) segmented = true;
+			if (b->arena_deferred) { if (size_deferred_arena(b)) segmented = true; }
+			else if (!segmented && b->arena_total >= b->arena_full && predict_arena_overflow(b)) segmented = true;
 			while (!segmented) { /* optimistic: all s^2 traceback bytes at once */
 				if (run_tile(b)) break;
 				if (!grow_arena(b)) segmented = true;
@@ -1656,6 +1737,7 @@ extern "C" void mwf_b200_batch_run(mwf_b200_batch_t *b)
 			if (segmented) run_tile_segmented(b);
 		} else if (b->kernel == MWF_B200_KERNEL_TILE && b->is_tb) { /* low-memory mode */
 			bool segmented = getenv("MWF_B200_TILE_SEGP") != 0 || b->d_snap != 0;
+			if (b->arena_deferred && size_deferred_arena(b)) segmented = true;
 			while (!segmented && !run_tile(b)) /* the unbanded pass does not fit the arena as s^2 bytes */
 				if (!grow_arena(b)) segmented = true;
 			if (segmented) {
