@@ -545,7 +545,7 @@ def main():
                           "e2e": S["e2e"], "parity": S["parity"]}
 
     # ---- single 150 kb pair (config 2), rank 0 -------------------------------------------------------------------------------
-    if rank == 0 and not args.no_single:
+    if rank == 0 and world == 1 and not args.no_single:  # (the single-pair legs belong to the N = 1 line; at N > 1 the other ranks would only wait)
         c2 = gold.get("config2-c")
         t, q = synth.make_pair(150000, 0.038, 900000)
         o2 = mw.opt_init(flag=mw.F_CIGAR)
@@ -595,7 +595,7 @@ def main():
         line["single_pair"] = sp
 
     # ---- 5 Mb pairs (config 4 and config 5 surrogates, one pair each), rank 0 --------------------------------------------
-    if rank == 0 and not args.no_large and not args.no_single:
+    if rank == 0 and world == 1 and not args.no_large and not args.no_single:
         large = {}
         for name, p, kw, gname, cpu_spec, what in (
                 ("config4", 0.0097, {"flag": mw.F_CIGAR, "step": 5000}, "config4-cp5000", (1000000, 0.0097, 424242, {"flag": 1, "step": 5000}),
