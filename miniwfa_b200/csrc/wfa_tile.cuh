@@ -938,21 +938,37 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const i
 	constexpr uint32_t CB = 1u << LCB;
 	int ho1[CPT], ho2[CPT], hx[CPT];
 	ldsv<CPT>(c.sb + qh.y, ho1); ldsv<CPT>(c.sb + qh.z, ho2); ldsv<CPT>(c.sb + qh.x, hx);
-	int A1[CPT + 2], A2[CPT + 2], C1[CPT + 2], C2[CPT + 2], bA1[CPT + 2], bA2[CPT + 2], bC1[CPT + 2], bC2[CPT + 2];
+	int A1[CPT + 2], A2[CPT + 2], C1[CPT + 2], C2[CPT + 2];
+	/* traceback bits (wf_next_tb, miniwfa.c:290-298): "the extension beat the opening", one bit per gap state of the cell a gap
+	 * value comes FROM.  cw = the four bits of this thread's own cells, already at the positions they take in the traceback byte
+	 * of the neighbouring diagonal -- byte j of cw: bit 3 = (ho1 < pe1), bit 5 = (ho2 < pe2) of cell j (read by cell j + 1 as its
+	 * E1 / E2 bits), bit 4 = (ho1 < pf1), bit 6 = (ho2 < pf2) (read by cell j - 1 as its F1 / F2 bits).  Each bit is the sign of
+	 * a difference, shifted in with one funnel shift (no compare + select pair per bit). */
+	uint32_t cw = 0;
 #pragma unroll
 	for (int j = 0; j < CPT; ++j) {
 		A1[j + 1] = max(ho1[j], pe1[j]), A2[j + 1] = max(ho2[j], pe2[j]);
 		C1[j + 1] = max(ho1[j], pf1[j]), C2[j + 1] = max(ho2[j], pf2[j]);
-		if (MODE != MODE_SCORE) bA1[j + 1] = ho1[j] < pe1[j], bA2[j + 1] = ho2[j] < pe2[j], bC1[j + 1] = ho1[j] < pf1[j], bC2[j + 1] = ho2[j] < pf2[j];
+	}
+	if (MODE != MODE_SCORE) {
+#pragma unroll
+		for (int j = CPT - 1; j >= 0; --j) { /* most significant byte first; every difference fits 32 bits (|values| <= 2^30 + small) */
+			if (j != CPT - 1) cw <<= 4; /* bits 2..0 of byte j + 1 and bit 7 of byte j stay 0 */
+			cw = __funnelshift_l((uint32_t)(ho2[j] - pf2[j]), cw, 1);
+			cw = __funnelshift_l((uint32_t)(ho2[j] - pe2[j]), cw, 1);
+			cw = __funnelshift_l((uint32_t)(ho1[j] - pf1[j]), cw, 1);
+			cw = __funnelshift_l((uint32_t)(ho1[j] - pe1[j]), cw, 1);
+		}
+		cw <<= 3;
 	}
 	A1[0] = __shfl_up_sync(0xffffffffu, A1[CPT], 1);
 	A2[0] = __shfl_up_sync(0xffffffffu, A2[CPT], 1);
 	C1[CPT + 1] = __shfl_down_sync(0xffffffffu, C1[1], 1);
 	C2[CPT + 1] = __shfl_down_sync(0xffffffffu, C2[1], 1);
+	uint32_t cl = 0, cr = 0; /* cw of the threads owning diagonals d0 - 1 (its last byte matters) and d0 + CPT (its first byte) */
 	if (MODE != MODE_SCORE) {
-		const int bl = __shfl_up_sync(0xffffffffu, bA1[CPT] | bA2[CPT] << 1, 1);
-		const int br = __shfl_down_sync(0xffffffffu, bC1[1] | bC2[1] << 1, 1);
-		bA1[0] = bl & 1, bA2[0] = bl >> 1, bC1[CPT + 1] = br & 1, bC2[CPT + 1] = br >> 1;
+		cl = __shfl_up_sync(0xffffffffu, cw, 1);
+		cr = __shfl_down_sync(0xffffffffu, cw, 1);
 	}
 	int h0[CPT], lim[CPT];
 	uint32_t tz[CPT];
@@ -963,7 +979,7 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const i
 		const int H = max(hxp, gmx); \
 		if (MODE != MODE_SCORE) { \
 			const int z = hxp >= gmx ? 0 : (e >= f ? (E1 >= E2 ? 1 : 3) : (F1 >= F2 ? 2 : 4)); \
-			tbw |= (uint32_t)(z | bA1[j] << 3 | bC1[j + 2] << 4 | bA2[j] << 5 | bC2[j + 2] << 6) << (8 * j); \
+			tbw |= (uint32_t)z << (8 * (j)); \
 		} \
 		pe1[j] = E1, pe2[j] = E2, pf1[j] = F1, pf2[j] = F2, h0[j] = H; \
 		const uint32_t tpb = min(((uint32_t)H << LCB) + c.c1, c.tend); \
@@ -981,11 +997,14 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const i
 		const int m1 = max(o1, x1), m2 = max(o2, x2);
 		if (c.left) A1[0] = m1, A2[0] = m2;
 		if (c.right) C1[CPT + 1] = m1, C2[CPT + 1] = m2;
-		if (MODE != MODE_SCORE) {
-			if (c.left) bA1[0] = o1 < x1, bA2[0] = o2 < x2;
-			if (c.right) bC1[CPT + 1] = o1 < x1, bC2[CPT + 1] = o2 < x2;
+		if (MODE != MODE_SCORE) { /* the neighbour warp's bits: E1 / E2 at bits 3 / 5 of the last byte, F1 / F2 at bits 4 / 6 of the first */
+			const uint32_t v = ((uint32_t)(o1 - x1) >> 31) | ((uint32_t)(o2 - x2) >> 31) << 2;
+			if (c.left) cl = v << (3 + 8 * (CPT - 1));
+			if (c.right) cr = v << 4;
 		}
 	}
+	if (MODE != MODE_SCORE) /* E bits from the diagonal below (bytes shifted up by one), F bits from the diagonal above */
+		tbw |= (((cw << 8) | ((cl >> (8 * (CPT - 1))) & 0xffu)) & 0x28282828u) | (((cw >> 8) | ((cr & 0xffu) << (8 * (CPT - 1)))) & 0x50505050u);
 	if (CPT == 4) { FAST2_CELL(0); FAST2_CELL((CPT - 1)); }
 	else {
 #pragma unroll
