@@ -385,8 +385,18 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 	}
 	} /* thread 0 */
 	__syncthreads();
-	if (PERSIST) {
-		for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) q_publish(P, (unsigned int)sh_emit[0] + j, slot, j); /* the block's tiles */
+	if (PERSIST) { /* the block's tiles: every payload of this thread first, then ONE release (a MEMBAR each would cost a large pair
+	                * with thousands of tiles per block tens of microseconds in which the whole GPU waits), then the sequence words */
+		const unsigned int base = (unsigned int)sh_emit[0];
+		const int n_emit = sh_emit[1];
+		for (int j = threadIdx.x; j < n_emit; j += blockDim.x) __stcg(P.q_items + ((base + j) & P.q_mask), make_int2(slot, j));
+		bool first = true;
+		for (int j = threadIdx.x; j < n_emit; j += blockDim.x) {
+			unsigned int *sq = P.q_seq + ((base + j) & P.q_mask);
+			if (first) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(sq), "r"(base + j + 1u) : "memory");
+			else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(sq), "r"(base + j + 1u) : "memory"); /* (after the release in program order) */
+			first = false;
+		}
 	} else {
 		for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) P.items[sh_emit[0] + j] = make_int2(slot, j);
 	}

@@ -10,7 +10,7 @@ from oracle import orc
 seed, n_cases = int(sys.argv[1]), int(sys.argv[2])
 max_len = int(sys.argv[3]) if len(sys.argv) > 3 else 6000
 rng = random.Random(seed)
-ENV = ["MWF_B200_TILE_CPT", "MWF_B200_TILE_THREADS", "MWF_B200_TILE_T", "MWF_B200_TILE_SEGP", "MWF_B200_TILE_WAVE", "MWF_B200_TILE_ARENA_MAX", "MWF_B200_TILE_SWITCH", "MWF_B200_LOWMEM_STREAMING"]
+ENV = ["MWF_B200_TILE_CPT", "MWF_B200_TILE_THREADS", "MWF_B200_TILE_T", "MWF_B200_TILE_SEGP", "MWF_B200_TILE_WAVE", "MWF_B200_TILE_ARENA_MAX", "MWF_B200_TILE_SWITCH", "MWF_B200_LOWMEM_STREAMING", "MWF_B200_TILE_PERSIST", "MWF_B200_TILE_FAST"]
 
 
 def mutate(t, p):
@@ -84,6 +84,10 @@ for case in range(n_cases):
         env.update(MWF_B200_TILE_WAVE=rng.randint(1, 4))
     if rng.random() < 0.15:
         env.update(MWF_B200_LOWMEM_STREAMING=1)
+    if rng.random() < 0.25:
+        env.update(MWF_B200_TILE_PERSIST=0)  # one plan + one tile launch per block instead of the persistent kernel
+    if rng.random() < 0.3:
+        env.update(MWF_B200_TILE_FAST=rng.choice([0, 1]))  # the interior step with all rows in shared memory / the first register-resident step
     for k, v in env.items():
         os.environ[k] = str(v)
     kw = rand_opt()
