@@ -22,20 +22,19 @@ def timed(cmd):
 
 
 with tempfile.TemporaryDirectory() as td:
-    for name, n_pairs, n, p, n_ref in (("150 bp reads, 2 %", 200000, 150, 0.02, 20000), ("100 kb pairs, 5 %", 256, 100000, 0.05, 2)):
+    for name, n_pairs, n, p, n_ref in (("150 bp reads, 2 %", 200000, 150, 0.02, 20000), ("150 bp reads, 2 %", 2000000, 150, 0.02, 20000), ("100 kb pairs, 5 %", 256, 100000, 0.05, 2)):
         pairs = [synth.make_pair(n, p, 7000 + i) for i in range(n_pairs)] if n > 1000 else None
-        if pairs is None:  # read-sized pairs: cut them out of a few long pairs (the generator costs ~1 ms per call)
-            pairs = []
-            t, q = synth.make_pair(n_pairs * n // 8, 0.0, 7000)
-            import random
-            rng = random.Random(1)
-            for i in range(n_pairs):
-                a = (i * n) % (len(t) - n)
-                s = bytearray(t[a:a + n])
-                for k in range(n):
-                    if rng.random() < p:
-                        s[k] = rng.choice(b"ACGT")
-                pairs.append((t[a:a + n], bytes(s)))
+        if pairs is None:  # read-sized pairs: windows of one long sequence, substitutions by a numpy mask
+            import numpy as np
+            t, _ = synth.make_pair(4000000, 0.0, 7000)
+            ta = np.frombuffer(t, dtype=np.uint8)
+            rs = np.random.RandomState(1)
+            starts = rs.randint(0, len(t) - n, size=n_pairs)
+            T = ta[starts[:, None] + np.arange(n)[None, :]]
+            Q = T.copy()
+            m = rs.random_sample(Q.shape) < p
+            Q[m] = np.frombuffer(b"ACGT", dtype=np.uint8)[rs.randint(0, 4, size=int(m.sum()))]
+            pairs = [(T[i].tobytes(), Q[i].tobytes()) for i in range(n_pairs)]
         fa, fb = os.path.join(td, "a.fa"), os.path.join(td, "b.fa")
         write_fasta(fa, [x[0] for x in pairs]); write_fasta(fb, [x[1] for x in pairs])
         for flags in ([], ["-c"]):
