@@ -1249,14 +1249,14 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		ws_dev(&b->d_tctl, sizeof(TileCtl) * wp, b->dev);
 		b->items_cap = (size_t)wp * ((size_t)b->pitch / umax + 2);
 		ws_dev(&b->d_items, sizeof(int2) * b->items_cap, b->dev);
-		ws_dev(&b->d_tmisc, 128, b->dev);
+		ws_dev(&b->d_tmisc, 256, b->dev);
 		if (env_int("MWF_B200_TILE_PACK", 1)) {
 			ws_dev(&b->d_seqp, b->seq_bytes / 2 + (size_t)max_len / 4 + 512, b->dev); /* (slack at the end: the clamped probes of cells off the matrix read up to tl codes past a query) */
 			ws_dev(&b->d_packed, sizeof(int) * std::max(1, n_pairs), b->dev);
 			if (env_int("MWF_B200_TILE_FAST", 2) >= 2 && (long long)b->seq_bytes < (1LL << 28))
 				ws_dev(&b->d_seqp2, 2 * (b->seq_bytes / 2 + (size_t)max_len / 4 + 512), b->dev);
 		}
-		ws_host(&b->h_running, 2 * 128);
+		ws_host(&b->h_running, 2 * 256);
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[0], cudaEventDisableTiming));
 		CUDA_OK(cudaEventCreateWithFlags(&b->evc[1], cudaEventDisableTiming));
 		if (seg) { /* low-memory mode: checkpoints found by walking a high-memory pass (wfa_tile_checkpoint_kernel) */
@@ -1405,7 +1405,7 @@ static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j =
 	int err = 0;
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
-	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
+	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 256, b->stream));
 	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
 	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]); ++b->launches; }
 	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(PP[0], seg_j); ++b->launches; }
@@ -1446,7 +1446,7 @@ static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j =
  * kernel retires, and the host launches the other geometry. */
 static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j, bool score_kernel)
 {
-	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 128, b->stream));
+	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 256, b->stream));
 	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
 	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]); ++b->launches; }
 	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(PP[0], seg_j); ++b->launches; }
@@ -1463,7 +1463,7 @@ static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int
 		b->launches += 2;
 		CUDA_OK(cudaGetLastError());
 		int *hr = b->h_running;
-		CUDA_OK(cudaMemcpyAsync(hr, b->d_tmisc, 128, cudaMemcpyDeviceToHost, b->stream));
+		CUDA_OK(cudaMemcpyAsync(hr, b->d_tmisc, 192, cudaMemcpyDeviceToHost, b->stream));
 		CUDA_OK(cudaStreamSynchronize(b->stream));
 		const PersistCtl *pq = (const PersistCtl*)(hr + 24);
 		if (env_int("MWF_B200_DEBUG", 0))

@@ -62,6 +62,7 @@ struct PersistCtl {
 	int stop_req;      /* a planner asked for the other tile geometry: pairs park after their block in flight */
 	int switch_to;
 	int total_tiles;   /* sum of n_tiles over the blocks in flight */
+	int scratch;        /* target of the release that orders a tile's alive words */
 	int n_start, n_cut; /* pairs in flight when the launch began; blocks cut since (the total above is meaningful once every pair has been cut) */
 };
 
@@ -1403,7 +1404,9 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 			bool wrote_alive;
 			const int n_tiles = tile_item<MODE, CPT>(P, S, slot, tile, wrote_alive);
 			if (tid < 32) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); asm volatile("fence.proxy.async;" ::: "memory"); }
-			if (wrote_alive) __threadfence(); /* one block in eight: every thread has stored alive words */
+			if (wrote_alive) /* one block in eight: every thread has stored alive words.  A release on a scratch word orders them
+			                  * (MEMBAR.ALL.GPU) without the L1 invalidation __threadfence() would add */
+				asm volatile("red.release.gpu.global.add.s32 [%0], 0;" :: "l"(&P.pq->scratch) : "memory");
 			__syncthreads();
 			if (tid == 0) { /* release: the rows, the band logs and (through the barrier) what the other threads stored */
 				int prev;
