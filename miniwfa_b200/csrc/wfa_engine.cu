@@ -1012,6 +1012,7 @@ struct mwf_b200_batch {
 	unsigned int *d_qseq;
 	unsigned int q_mask;
 	bool persist;
+	int seg_K;             /* traceback segments recomputed at once (virtual slots: seg_K x wave_pairs) */
 	double s_est;          /* a high estimate of the largest score of the batch (shared 13-mers), 0 when unknown */
 	bool arena_deferred;   /* a few very long pairs: the traceback arena is sized in mwf_b200_batch_run, from the pairs' shared 13-mers */
 	unsigned char *d_tmisc; /* TileCounters[2] @0, n_running @32, arena_used @64 */
@@ -1222,7 +1223,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	ws_dev(&b->d_order, sizeof(int) * std::max(1, n_pairs), b->dev);
 	ws_dev(&b->d_ctl, 64, b->dev);
 	b->d_ring = 0, b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
-	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->q_mask = 0, b->persist = false, b->arena_deferred = false, b->s_est = 0, b->d_tmisc = 0, b->h_running = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->q_mask = 0, b->persist = false, b->arena_deferred = false, b->s_est = 0, b->seg_K = 1, b->d_tmisc = 0, b->h_running = 0;
 	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0, b->wave_pairs = 0;
 	if (b->is_tb) ws_dev(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw), b->dev);
 	if (pref == MWF_B200_KERNEL_TILE) {
@@ -1397,17 +1398,19 @@ static void launch_grid(mwf_b200_batch_t *b, KParams P, int pair)
  * The number of running pairs and of tiles per launch is read back one chunk of launches behind, so the device never waits for
  * the host; the tile count picks the geometry of the next chunk. */
 /* returns the error bits the planner raised during the pass: 1 << TS_ARENA, 1 << TS_SHRINK */
-static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j, bool score_kernel);
+static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j, bool score_kernel, int group);
 
-static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false)
+/* group > 1 (persistent kernel only): segments seg_j, seg_j - 1, ..., seg_j - group + 1 of every pair are recomputed in one pass,
+ * each on its own virtual slot (state, TileCtl, alive words), so that a few very long pairs keep the GPU full */
+static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false, int group = 1)
 {
-	if (b->persist) return tile_pass_persist(b, PP, np, seg_j, score_kernel);
+	if (b->persist) return tile_pass_persist(b, PP, np, seg_j, score_kernel, group);
 	int err = 0;
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
 	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 256, b->stream));
 	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
-	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]); ++b->launches; }
+	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0], 0); ++b->launches; }
 	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(PP[0], seg_j); ++b->launches; }
 	CUDA_OK(cudaGetLastError());
 	int it = 0, g = b->n_geom > 1 && np >= 16 ? 1 : 0;
@@ -1444,18 +1447,23 @@ static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j =
  * run the throughput geometry throughout; a few large pairs start in the latency geometry, and the planner asks for the other
  * one when the number of tiles in flight crosses `many` (back below many / 2): the pairs park after their block in flight, the
  * kernel retires, and the host launches the other geometry. */
-static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j, bool score_kernel)
+static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np_pairs, int seg_j, bool score_kernel, int group)
 {
+	const int np = np_pairs * group, vmod = group > 1 ? np_pairs : 0; /* np: (virtual) slots of this pass */
+	TParams P0 = PP[0];
+	P0.n_pairs = np, P0.vmod = vmod;
 	CUDA_OK(cudaMemsetAsync(b->d_tmisc, 0, 256, b->stream));
 	CUDA_OK(cudaMemsetAsync(b->d_alive, 0, (size_t)np * b->pitch * 4, b->stream));
-	if (seg_j <= 0) { wfa_tile_init_kernel<<<np, 128, 0, b->stream>>>(PP[0]); ++b->launches; }
-	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(PP[0], seg_j); ++b->launches; }
+	if (seg_j < 0) { wfa_tile_init_kernel<<<np_pairs, 128, 0, b->stream>>>(P0, 0); ++b->launches; }
+	else if (seg_j < group) { wfa_tile_init_kernel<<<np_pairs, 128, 0, b->stream>>>(P0, seg_j * np_pairs); ++b->launches; } /* the slots of segment 0 */
+	if (seg_j >= 0) { wfa_tile_segstart_kernel<<<dim3(np, seg_j > 0 ? 64 : 1), 256, 0, b->stream>>>(P0, seg_j); ++b->launches; }
 	CUDA_OK(cudaGetLastError());
 	const bool may_switch = b->n_geom > 1 && np < 16;
 	int g = b->n_geom > 1 && np >= 16 ? 1 : 0;
 	for (int round = 0;; ++round) {
 		TParams P = PP[g];
 		const mwf_b200_batch::TileGeom &G = b->geom[g];
+		P.n_pairs = np, P.vmod = vmod;
 		P.geom_id = g, P.n_geom = may_switch ? 2 : 1, P.many = env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
 		CUDA_OK(cudaMemsetAsync(b->d_qseq, 0, sizeof(unsigned int) * ((size_t)b->q_mask + 1), b->stream));
 		wfa_tile_persist_begin_kernel<<<1, 256, 0, b->stream>>>(P, G.grid_p);
@@ -1566,7 +1574,7 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		b->snapdir_stride = (int)(b->max_sbound / b->seg_P + 2);
 		const long long half = (long long)((double)free_b * 0.45) & ~255LL;
 		const long long width = b->max_len + 2LL * b->pen.nring + 2LL * TILE_TMAX + 16;
-		long long need = (long long)(b->seg_P + 2 * TILE_TMAX) * width * wp; /* traceback rows of one segment */
+		long long need = (long long)(b->seg_P + 2 * TILE_TMAX) * width * wp; /* traceback rows of one segment (at the full width: a loose bound) */
 		if (lowmem) need = half; /* ... and of pass 2, which is banded only while the reference's checkpoint matching keeps up: with
 		                            step below the penalties two snapshots can share a checkpoint and the band stops collapsing (:413-416) */
 		b->arena_total = std::min(half, (need + 255) & ~255LL);
@@ -1580,11 +1588,33 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 			snap_bytes = std::min(snap_bytes, (long long)est & ~255LL);
 		}
 		b->snap_words = snap_bytes / 4;
+		/* a few very long pairs: recompute several segments at once, each on a virtual slot of its own (state, TileCtl, alive
+		 * words, queue room): a single pair's block of scores leaves the last wave of tiles nearly empty, K segments interleave */
+		b->seg_K = 1;
+		if (!lowmem && b->persist && wp <= 8) {
+			const size_t per_slot = (size_t)2 * b->tR * b->pitch * 4 + (size_t)b->pitch * 4;
+			int K = std::max(1, std::min(env_int("MWF_B200_TILE_SEGPAR", 3), 8));
+			while (K > 1 && (double)K * wp * per_slot > 0.1 * (double)free_b) --K;
+			if (K > 1) {
+				b->seg_K = K;
+				ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_tctl); ws_free(b->d_qitems); ws_free(b->d_qseq);
+				if (ws_dev(&b->d_state, (size_t)K * wp * 2 * b->tR * b->pitch * 4, b->dev))
+					CUDA_OK(cudaMemsetAsync(b->d_state, 0xC0, (size_t)K * wp * 2 * b->tR * b->pitch * 4, b->stream));
+				ws_dev(&b->d_alive, (size_t)K * wp * b->pitch * 4, b->dev);
+				ws_dev(&b->d_tctl, sizeof(TileCtl) * K * wp, b->dev);
+				size_t need_q = 2 * ((size_t)K * b->items_cap + (size_t)K * wp + (size_t)std::max(b->geom[0].grid_p, b->geom[b->n_geom - 1].grid_p)) + 4096, cap = 1;
+				while (cap < need_q) cap <<= 1;
+				b->q_mask = (unsigned int)(cap - 1);
+				ws_dev(&b->d_qitems, sizeof(int2) * cap, b->dev);
+				ws_dev(&b->d_qseq, sizeof(unsigned int) * cap, b->dev);
+				b->arena_total = std::min(half, ((long long)K * need + 255) & ~255LL);
+			}
+		}
 		ws_dev(&b->d_arena, (size_t)b->arena_total, b->dev);
 		ws_dev(&b->d_snap, (size_t)b->snap_words * 4, b->dev);
 		ws_dev(&b->d_snapdir, sizeof(SnapDir) * (size_t)b->snapdir_stride * wp, b->dev);
 		ws_dev(&b->d_nsnap, sizeof(int) * wp, b->dev);
-		ws_dev(&b->d_sstop, sizeof(int) * wp, b->dev);
+		ws_dev(&b->d_sstop, sizeof(int) * wp * b->seg_K, b->dev);
 		ws_dev(&b->d_trace, sizeof(TraceState) * wp, b->dev);
 		ws_host(&b->h_nsnap, sizeof(int) * wp);
 	}
@@ -1634,14 +1664,18 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 		/* backward: one segment at a time, traceback bytes of that segment only */
 		for (int g = 0; g < 2; ++g)
 			PP[g].is_tb = 1, PP[g].snap_take = 0, PP[g].s_stop = b->d_sstop, PP[g].max_s = 0, PP[g].max_iter = 0;
-		for (int j = max_seg; j >= 0; --j) {
+		const int K = b->seg_K;
+		for (int j = max_seg; j >= 0; j -= K) {
+			const int kk = std::min(K, j + 1); /* segments j, j - 1, ..., j - kk + 1 in one pass */
 			SEG_NOW(t0x);
-			if (tile_pass(b, PP, np, j, false)) die("device workspace exhausted (traceback bytes of one segment); lower MWF_B200_TILE_SEGP");
+			if (tile_pass(b, PP, np, j, false, kk)) die("device workspace exhausted (traceback bytes of one segment); lower MWF_B200_TILE_SEGP");
 			SEG_NOW(t1x); t_pass += t1x - t0x;
-			if (lowmem) wfa_tile_ckpt_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
-			else wfa_tile_trace_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j);
+			for (int k = 0; k < kk; ++k) { /* the walks, in order: each resumes where the one above it stopped */
+				if (lowmem) wfa_tile_ckpt_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j - k);
+				else wfa_tile_trace_seg_kernel<<<np, 32, 0, b->stream>>>(PP[0], j - k, k * np);
+				++b->launches;
+			}
 			CUDA_OK(cudaGetLastError());
-			++b->launches;
 			SEG_NOW(t0x); t_walk += t0x - t1x;
 		}
 		if (timing) fprintf(stderr, "[mwf_b200] segmented traceback: forward pass with snapshots %.1f ms, %d segments recomputed %.1f ms, walked %.1f ms\n", t_fwd, max_seg + 1, t_pass, t_walk);

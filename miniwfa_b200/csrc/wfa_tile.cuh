@@ -107,6 +107,7 @@ struct TParams {
 	int2 *q_items;
 	unsigned int *q_seq;
 	unsigned int q_mask;
+	int vmod;                  /* > 0: slot v stands for pair slot v % vmod (several traceback segments of a pair recomputed at once) */
 	int geom_id, n_geom, many; /* this launch's geometry (0 latency, 1 throughput); switch above `many` / below many / 2 tiles in flight */
 	/* segmented traceback */
 	int snap_P, snapdir_stride, snap_take; /* snap_take: save a snapshot whenever s is a multiple of snap_P (a multiple of 256) */
@@ -122,6 +123,9 @@ struct TParams {
 	int4 tabE1[TILE_EDEPTH_MAX]; /* [s % (e1+1)] = {E1[s-e1], F1[s-e1], E1[s], F1[s]} */
 	int4 tabE2[TILE_EDEPTH_MAX]; /* [s % (e2+1)] = {E2[s-e2], F2[s-e2], E2[s], F2[s]} */
 };
+
+/* the pair slot behind a (possibly virtual) slot: per-pair arrays -- order, rowtab, snapshots, trace state -- are indexed by it */
+__device__ __forceinline__ int pair_slot(const TParams &P, int slot) { return P.vmod > 0 ? slot % P.vmod : slot; }
 
 /* index of diagonal 0 in a state row: independent of the tile geometry, so that the geometry may change between launches */
 __device__ __forceinline__ int tile_doff(const TParams &P, int tl) { return tl + P.pen.nring + TILE_TMAX + 8; }
@@ -173,9 +177,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 /* score 0 (wf_stripe_init, miniwfa.c:103-121, and the first extend)                            */
 /* ------------------------------------------------------------------------------------------ */
 
-__global__ void wfa_tile_init_kernel(const TParams P)
+__global__ void wfa_tile_init_kernel(const TParams P, int slot0)
 {
-	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	const int slot = slot0 + blockIdx.x, pi = P.order[P.pair0 + pair_slot(P, slot)];
 	const PairDesc pd = P.pairs[pi];
 	const int n = P.pen.nring, doff = tile_doff(P, pd.tl);
 	int32_t *st = P.state + (size_t)slot * 2 * P.R * P.pitch;
@@ -237,7 +241,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 	__shared__ int widths[TILE_TMAX];
 	__shared__ long long sh_row[2];
 	__shared__ int sh_emit[4]; /* items base, n_tiles, first score of the rows, number of rows */
-	const int pi = P.order[P.pair0 + slot];
+	const int pslot = pair_slot(P, slot), pi = P.order[P.pair0 + pslot];
 	TileCtl *c = P.ctl + slot;
 #define CL(f) __ldcg(&c->f) /* TileCtl is written by other SMs inside the persistent kernel: read it from L2 */
 	__syncthreads(); /* (the shared words above may still be read by the previous call) */
@@ -402,7 +406,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 		for (int j = threadIdx.x; j < sh_emit[1]; j += blockDim.x) P.items[sh_emit[0] + j] = make_int2(slot, j);
 	}
 	if (threadIdx.x < sh_emit[3]) /* wf_tb_add (:33-44): where the traceback row of every score of the block starts */
-		P.rowtab[(size_t)slot * P.rowtab_stride + sh_emit[2] + 1 + threadIdx.x] = sh_row[0] + (long long)threadIdx.x * sh_row[1];
+		P.rowtab[(size_t)pslot * P.rowtab_stride + sh_emit[2] + 1 + threadIdx.x] = sh_row[0] + (long long)threadIdx.x * sh_row[1];
 }
 #undef CL
 
@@ -1156,7 +1160,7 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	const int n = P.pen.nring, d1 = P.pen.e1 + 1, d2 = P.pen.e2 + 1;
 	const bool no_left = tid == 0, no_right = tid == NT - 1;
 	TileCtl *ctl = P.ctl + slot;
-	const int pi = P.order[P.pair0 + slot];
+	const int pi = P.order[P.pair0 + pair_slot(P, slot)];
 	const PairDesc pd = P.pairs[pi];
 	const int tl = pd.tl, ql = pd.ql, doff = tile_doff(P, tl), dfin = ql - tl;
 	/* (fields of TileCtl and the alive words are written by other SMs inside the persistent kernel: read from L2, never through L1) */
@@ -1555,13 +1559,14 @@ __global__ void wfa_tile_trace_begin_kernel(const TParams P)
 
 /* start segment j of every pair that has one: segment 0 starts at score 0 (wfa_tile_init_kernel has run), segment j > 0 at
  * snapshot j-1, whose rows go back into state buffer 0.  grid = (n_pairs, copy CTAs) */
-__global__ void wfa_tile_segstart_kernel(const TParams P, int j)
+__global__ void wfa_tile_segstart_kernel(const TParams P, int j_first)
 {
-	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot];
+	/* slot v of a group of segments: segment j_first - v / vmod of pair slot v % vmod (one segment per slot when vmod = 0) */
+	const int slot = blockIdx.x, ps = pair_slot(P, slot), j = j_first - (P.vmod > 0 ? slot / P.vmod : 0), pi = P.order[P.pair0 + ps];
 	TileCtl *c = P.ctl + slot;
-	const TraceState *ts = P.trace + slot;
-	const int n_snap = P.n_snap[slot];
-	const bool active = ts->fwd_status == TS_DONE && j <= n_snap;
+	const TraceState *ts = P.trace + ps;
+	const int n_snap = P.n_snap[ps];
+	const bool active = ts->fwd_status == TS_DONE && j <= n_snap && j >= 0;
 	if (j == 0) {
 		if (blockIdx.y == 0 && threadIdx.x == 0) {
 			if (!active && c->status == TS_RUN) { c->status = TS_IDLE; atomicSub(P.n_running, 1); }
@@ -1570,7 +1575,7 @@ __global__ void wfa_tile_segstart_kernel(const TParams P, int j)
 		return;
 	}
 	if (!active) { if (blockIdx.y == 0 && threadIdx.x == 0) c->status = TS_IDLE; return; }
-	const SnapDir d = P.snapdir[(size_t)slot * P.snapdir_stride + (j - 1)];
+	const SnapDir d = P.snapdir[(size_t)ps * P.snapdir_stride + (j - 1)];
 	int32_t *st = P.state + (size_t)slot * 2 * P.R * P.pitch;
 	const int32_t *src = P.snap_arena + d.off;
 	const int n4 = d.rowsize >> 2;
@@ -1591,13 +1596,13 @@ __global__ void wfa_tile_segstart_kernel(const TParams P, int j)
 
 /* wf_traceback (miniwfa.c:329-377) over the traceback bytes of segment j only: the walk stops when it needs a row at or
  * below the segment's first score and resumes there in the next (earlier) segment.  One warp per pair. */
-__global__ void wfa_tile_trace_seg_kernel(const TParams P, int j)
+__global__ void wfa_tile_trace_seg_kernel(const TParams P, int j, int vslot0)
 {
 	const int slot = blockIdx.x, pi = P.order[P.pair0 + slot], lane = threadIdx.x & 31;
 	TraceState *tsp = P.trace + slot;
 	const int n_snap = P.n_snap[slot];
 	if (tsp->fwd_status != TS_DONE || j > n_snap) return;
-	const TileCtl *c = P.ctl + slot;
+	const TileCtl *c = P.ctl + vslot0 + slot; /* the (virtual) slot that recomputed segment j */
 	const PairDesc pd = P.pairs[pi];
 	const uint8_t *T8 = P.seq + pd.t_off, *Q8 = P.seq + pd.q_off;
 	const long long *rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
