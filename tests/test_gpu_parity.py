@@ -517,11 +517,15 @@ def test_segmented_traceback(monkeypatch):
         monkeypatch.setenv("MWF_B200_TILE_WAVE", str(wave))
         for kw, w in zip(modes, want):
             assert mw.wfa_exact_batch(mw.opt_init(**kw), pairs) == w, (segp, cap, wave, kw)
-    # single pairs take the 1-cell-per-thread geometry
+    # single pairs take the latency geometry, and several segments are recomputed per pass on virtual slots
     monkeypatch.setenv("MWF_B200_TILE_SEGP", "256")
     monkeypatch.setenv("MWF_B200_TILE_ARENA_MAX", "0")
     for (t, q), w in zip(pairs[3:9], want[0][3:9]):
         assert mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR), t, q) == w
+    for par in (1, 2, 5):  # segments per pass; a batch of up to 8 pairs is spread over par x pairs virtual slots
+        monkeypatch.setenv("MWF_B200_TILE_SEGPAR", str(par))
+        assert mw.wfa_exact_batch(mw.opt_init(flag=mw.F_CIGAR), pairs[9:15]) == want[0][9:15], par
+        assert mw.wfa_exact(mw.opt_init(flag=mw.F_CIGAR, max_s=900), *pairs[12]) == want[2][12], par
 
 
 def test_concurrent_host_threads():
