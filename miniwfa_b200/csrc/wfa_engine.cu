@@ -1254,7 +1254,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		if (env_int("MWF_B200_TILE_PACK", 1)) {
 			ws_dev(&b->d_seqp, b->seq_bytes / 2 + (size_t)max_len / 4 + 512, b->dev); /* (slack at the end: the clamped probes of cells off the matrix read up to tl codes past a query) */
 			ws_dev(&b->d_packed, sizeof(int) * std::max(1, n_pairs), b->dev);
-			if (env_int("MWF_B200_TILE_FAST", 2) >= 2 && (long long)b->seq_bytes < (1LL << 28))
+			if (env_int("MWF_B200_TILE_FAST", 2) >= 2)
 				ws_dev(&b->d_seqp2, 2 * (b->seq_bytes / 2 + (size_t)max_len / 4 + 512), b->dev);
 		}
 		ws_host(&b->h_running, 2 * 256);
@@ -1508,8 +1508,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
-	/* (the fast path addresses the sequences by 32-bit bit positions inside the sequence buffer) */
-	P.fast = env_int("MWF_B200_TILE_FAST", 2) * (int)(b->pen.e1 <= 2 && b->pen.e2 <= 2 && (long long)b->seq_bytes < (1LL << 28));
+	P.fast = env_int("MWF_B200_TILE_FAST", 2) * (int)(b->pen.e1 <= 2 && b->pen.e2 <= 2);
 	if (P.fast >= 2 && !b->d_seqp2) P.fast = 1;
 	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
