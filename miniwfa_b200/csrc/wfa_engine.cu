@@ -1254,7 +1254,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 		if (env_int("MWF_B200_TILE_PACK", 1)) {
 			ws_dev(&b->d_seqp, b->seq_bytes / 2 + (size_t)max_len / 4 + 512, b->dev); /* (slack at the end: the clamped probes of cells off the matrix read up to tl codes past a query) */
 			ws_dev(&b->d_packed, sizeof(int) * std::max(1, n_pairs), b->dev);
-			if (env_int("MWF_B200_TILE_FAST", 2) >= 2)
+			if (env_int("MWF_B200_TILE_FAST", 2) >= 2 && (long long)b->seq_bytes < (1LL << 28))
 				ws_dev(&b->d_seqp2, 2 * (b->seq_bytes / 2 + (size_t)max_len / 4 + 512), b->dev);
 		}
 		ws_host(&b->h_running, 2 * 256);
@@ -1508,7 +1508,8 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
 	P.s_limit = b->s_limit;
-	P.fast = env_int("MWF_B200_TILE_FAST", 2) * (int)(b->pen.e1 <= 2 && b->pen.e2 <= 2);
+	/* (the fast path addresses the sequences by 32-bit bit positions inside the sequence buffer) */
+	P.fast = env_int("MWF_B200_TILE_FAST", 2) * (int)(b->pen.e1 <= 2 && b->pen.e2 <= 2 && (long long)b->seq_bytes < (1LL << 28));
 	if (P.fast >= 2 && !b->d_seqp2) P.fast = 1;
 	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
@@ -1983,6 +1984,24 @@ extern "C" void mwf_wfa_exact_batch(void *km, const mwf_opt_t *opt, int32_t n_pa
                                     const int32_t *ql, const char *const *qs, mwf_rst_t *r)
 {
 	const int n_dev = batch_devices(n_pairs, tl, ql);
+	{ /* The register-resident steps of the tile engine address the sequences of a batch by 32-bit bit positions, which holds for
+	   * up to 2^28 bytes of sequence per device batch (about 1300 pairs of 100 kb); a larger submission is cut into consecutive
+	   * parts of at most that size per device -- the same results, and the same rate, as one batch would give */
+		const double cap = 200e6 * n_dev;
+		double bytes = 0;
+		for (int i = 0; i < n_pairs; ++i) bytes += (double)tl[i] + ql[i] + 160;
+		if (bytes > cap && n_pairs > 1) {
+			int i0 = 0;
+			while (i0 < n_pairs) {
+				double part = 0;
+				int i1 = i0;
+				while (i1 < n_pairs && (i1 == i0 || part + tl[i1] + ql[i1] + 160 <= cap)) part += (double)tl[i1] + ql[i1] + 160, ++i1;
+				mwf_wfa_exact_batch(km, opt, i1 - i0, tl + i0, ts + i0, ql + i0, qs + i0, r + i0);
+				i0 = i1;
+			}
+			return;
+		}
+	}
 	if (n_dev <= 1) { exact_batch_one_device(km, opt, n_pairs, tl, ts, ql, qs, r); return; }
 	const int dev0 = mwf_b200_get_device(), vis = mwf_b200_device_count();
 	struct Shard { std::vector<int> idx; std::vector<int32_t> tl, ql; std::vector<const char*> ts, qs; std::vector<mwf_rst_t> r; mwf_b200_batch_t *b; double load; };

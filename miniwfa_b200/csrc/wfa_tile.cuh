@@ -229,6 +229,22 @@ __device__ __forceinline__ void q_publish(const TParams &P, unsigned int ticket,
 	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(P.q_seq + i), "r"(ticket + 1u) : "memory"); /* (a release, not __threadfence(): that one also drops the SM's L1) */
 }
 
+/* take a ticket and wait for its item (one thread per CTA).  No acquire fence: it would drop the L1 lines of all four CTAs of the
+ * SM (the sequence windows) on every item.  The payload load is issued only after the sequence word has been seen, the producer
+ * released it after the payload, and everything other SMs write inside this kernel is read past L1 (ld.cg, bulk copies).
+ * Not inlined: the tile kernel sits at its register limit. */
+__device__ __noinline__ int2 q_take(const TParams &P)
+{
+	const unsigned int ticket = atomicAdd(&P.pq->head, 1u), i = ticket & P.q_mask;
+	unsigned int ns = 32, spins = 0;
+	while (ld_volatile_u32(P.q_seq + i) != ticket + 1u) {
+		__nanosleep(ns);
+		if (ns < 256) ns <<= 1;
+		if (++spins == 0x30000000u) __trap(); /* minutes without an item: a lost hand-over must end as a launch failure, not as a device that hangs for good */
+	}
+	return __ldcg(P.q_items + i);
+}
+
 /* The planner of one pair: replay the block that has just finished, trim, cut the next block and hand out its tiles.
  * PERSIST = false: wfa_plan_kernel, one CTA per pair between two launches of the tile kernel, tiles appended to the item list
  * of launch `it`.  PERSIST = true: called inside wfa_tile_persist_kernel by the CTA that finished the last tile of the pair's
@@ -1198,7 +1214,6 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	const int c = CPT * tid, d0 = idx0 + c - doff;
 	const bool useful = c >= HL && c < HL + ulen;
 	const bool special = left_edge || right_edge || (dfin >= idx0 - doff && dfin < idx0 - doff + W); /* flags matter */
-	const bool fits32 = (unsigned long long)(pd.q_off - pd.t_off) * 8ull + 8ull * ((unsigned long long)tl + ql + 64) < (1ull << 31); /* the register-resident steps address the pair by 32-bit bit positions */
 	uint8_t *tbp = 0; /* traceback bytes of this thread's diagonals at the block's first score (wf_tb_add, :33-44) */
 	long long tb_pitch = 0;
 	if (MODE == MODE_TB) tbp = P.arena + __ldcg(&ctl->row_base) + (idx0 + c), tb_pitch = __ldcg(&ctl->row_size);
@@ -1232,7 +1247,7 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	/* ---- Tb fused next+extend steps ---- */
 	CellOut<CPT> o;
 	bool stepped = false;
-	if (!special && Tb > 0 && fits32 && P.fast >= 2 && code_bits != 0 && P.pen.e1 == 2 && P.pen.e2 == 1) { /* interior tile, packed codes, default gap extensions */
+	if (!special && Tb > 0 && P.fast >= 2 && code_bits != 0 && P.pen.e1 == 2 && P.pen.e2 == 1) { /* interior tile, packed codes, default gap extensions */
 		Fast2Ctx<CPT> c;
 		const uint32_t rb = 4u * W, cb = (uint32_t)code_bits;
 		const int warp = tid >> 5;
@@ -1241,8 +1256,8 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 		c.nbh = sb + (lane == 0 ? -4 : 4 * CPT);
 		c.xr = xch + 16u * (warp + 1) + (lane == 0 ? 0u : 8u);                    /* side 0: from lane 31 of the warp before; side 1: from lane 0 of the next */
 		c.xw = xch + (lane == 0 ? 16u * warp + 8u : 16u * (warp + 2));           /* lane 0 writes side 1 of the warp before, lane 31 side 0 of the next */
-		c.seqw = P.seqp2 + (sv.T - P.seqp); /* bit positions count from the pair's own target: 32 bits do for any batch size */
-		const uint32_t tbits = 0, qbits = (uint32_t)(sv.Q - sv.T) << 5;
+		c.seqw = P.seqp2;
+		const uint32_t tbits = (uint32_t)(sv.T - P.seqp) << 5, qbits = (uint32_t)(sv.Q - P.seqp) << 5;
 		c.c1 = tbits + cb, c.tend = tbits + cb * (uint32_t)tl, c.dq0 = qbits - tbits + cb * (uint32_t)d0;
 #pragma unroll
 		for (int j = 0; j < CPT; ++j) c.kend[j] = (int)cb * min(tl - 1, ql - 1 - (d0 + j)) + (int)c.c1;
@@ -1254,7 +1269,7 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	}
 	if constexpr (CPT == 4) {
 		if (stepped) {
-		} else if (!special && Tb > 0 && fits32 && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
+		} else if (!special && Tb > 0 && P.fast) { /* interior tile, throughput geometry, gap rows in registers */
 			FastCtx c;
 			const uint32_t rb = 4u * W;
 			c.sb = sb, c.left = lane == 0, c.right = lane == 31, c.bnd_lane = lane == 0 || lane == 31;
@@ -1264,9 +1279,9 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 			c.nb1 = c.nb + (lane == 0 ? 0u : c.f1off), c.nb2 = c.nb + (lane == 0 ? 0u : c.f2off);
 			c.bs1 = lane == 31 ? sb + 12 : sb + c.f1off, c.bs2 = lane == 31 ? sb + 12 : sb + c.f2off;
 			c.lcb = sv.s_amt, c.cb = 1u << sv.s_amt, c.cb2 = 2u << sv.s_amt, c.cb3 = 3u << sv.s_amt;
-			c.seqw = sv.T; /* bit positions count from the pair's own target */
-			c.tbits = 0;
-			c.dq0 = ((uint32_t)(sv.Q - sv.T) << 5) + ((uint32_t)d0 << sv.s_amt);
+			c.seqw = code_bits ? P.seqp : reinterpret_cast<const uint32_t*>(P.seq);
+			c.tbits = (uint32_t)(sv.T - c.seqw) << 5;
+			c.dq0 = ((uint32_t)(sv.Q - c.seqw) << 5) - c.tbits + ((uint32_t)d0 << sv.s_amt);
 			c.d0 = d0;
 			c.tl = tl, c.ql = ql, c.tlm1 = tl - 1, c.qlm1d0 = ql - 1 - d0;
 			const int e1 = P.pen.e1, e2 = P.pen.e2;
@@ -1391,13 +1406,7 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) {
-			const unsigned int ticket = atomicAdd(&P.pq->head, 1u), i = ticket & P.q_mask;
-			unsigned int ns = 32;
-			while (ld_volatile_u32(P.q_seq + i) != ticket + 1u) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
-			/* no acquire fence here: it would drop the L1 lines of all four CTAs of the SM (the sequence windows) on every item.
-			 * The payload load below is issued only after the sequence word has been seen, the producer released it after the
-			 * payload, and everything other SMs write inside this kernel is read past L1 (ld.cg, bulk copies). */
-			const int2 v = __ldcg(P.q_items + i);
+			const int2 v = q_take(P);
 			S.sc[3] = v.x, S.sc[4] = v.y, S.sc[5] = 0;
 		}
 		__syncthreads();
