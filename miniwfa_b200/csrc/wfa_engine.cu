@@ -603,7 +603,11 @@ __device__ bool trace_checkpoints(const Job &J, const Pen &pen, int n_snap, int 
  * of the two insertion and the two deletion states.  Lanes 0..8 fetch all nine as soon as the current cell is known, so the
  * row-table lookup and the byte are in flight during the match run of the cell instead of after it, and the match runs' sequence
  * lines are prefetched 256 bases ahead (150 kb pair, 10 924 CIGAR operations: 7.5 -> 6.8 ms). */
-__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state)
+#define TB_ROWWIN 2048 /* entries of the row table a traceback warp keeps in shared memory */
+
+/* rtw: TB_ROWWIN entries of shared memory for a sliding window of the row table (the walk needs rowtab[row - penalty] before every
+ * traceback byte: from shared memory that is one dependent global load less per step), or null */
+__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state, long long *rtw = 0)
 {
 	const int lane = threadIdx.x & 31, doff = J.doff;
 	int i = J.ql - 1, k = J.tl - 1, row = s_final, n_out = 0, cur_op = -1;
@@ -613,7 +617,20 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 	const int cg = (lane - 1) >> 1, copen = (lane - 1) & 1;
 	const int cpen = lane == 0 ? pen.x : (cg & 1) ? (copen ? pen.oe2 : pen.e2) : (copen ? pen.oe1 : pen.e1);
 	const int cdd = lane == 0 ? 0 : cg < 2 ? -1 : 1; /* an insertion steps to diagonal d - 1, a deletion to d + 1 */
-	int x = row >= 1 ? (int)__ldcg(J.arena + J.rowtab[row] + (i - k + doff)) : 0; /* the byte of (row, i - k): a match run keeps the diagonal */
+	int win_lo = 0x7fffffff; /* rows [win_lo, ...] of the table are in rtw (rows only go down) */
+	const int maxpen = max(pen.x, max(pen.oe1, pen.oe2));
+#define RT(row_) ((row_) >= win_lo ? rtw[(row_) - win_lo] : J.rowtab[row_])
+#define RT_REFILL() do { \
+		if (rtw && win_lo > 1 && row - maxpen < win_lo) { /* slide the window down to end at the current row */ \
+			const int nlo = max(1, row - TB_ROWWIN + 1); \
+			__syncwarp(); \
+			for (int r_ = nlo + lane; r_ <= row; r_ += 32) rtw[r_ - nlo] = J.rowtab[r_]; \
+			__syncwarp(); \
+			win_lo = nlo; \
+		} \
+	} while (0)
+	RT_REFILL();
+	int x = row >= 1 ? (int)__ldcg(J.arena + RT(row) + (i - k + doff)) : 0; /* the byte of (row, i - k): a match run keeps the diagonal */
 #define CIG_PUSH(op_, len_) do { \
 		if ((op_) == cur_op) cur_len += (len_); \
 		else { if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; } cur_op = (op_), cur_len = (len_); } \
@@ -622,7 +639,7 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 #define SUCCESSORS(dst_) do { \
 		(dst_) = 0; \
 		if (lane < 9 && row - cpen >= 1) { \
-			long long off_ = J.rowtab[row - cpen] + (i - k + cdd + doff); \
+			long long off_ = RT(row - cpen) + (i - k + cdd + doff); \
 			off_ = off_ < 0 ? 0 : off_ >= J.arena_cap ? J.arena_cap - 1 : off_; \
 			(dst_) = __ldcg(J.arena + off_); \
 		} \
@@ -655,10 +672,13 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 		if (state > 0 && !ext) ++csel;
 		last = (state > 0 && ext) ? state : 0;
 		x = __shfl_sync(0xffffffffu, xs, csel);
+		RT_REFILL();
 		SUCCESSORS(xs_next); /* (issuing these before the shuffle was slower on the box: 8.1 ms against 6.8 ms on the 150 kb pair) */
 		xs = xs_next;
 	}
 #undef SUCCESSORS
+#undef RT_REFILL
+#undef RT
 	end_state[0] = row, end_state[1] = i, end_state[2] = k; /* :367 */
 	if (i >= 0) CIG_PUSH(1, (uint32_t)(i + 1));       /* :368 */
 	else if (k >= 0) CIG_PUSH(2, (uint32_t)(k + 1));  /* :369 */

@@ -1541,7 +1541,8 @@ __global__ void wfa_tile_traceback_kernel(const TParams P)
 	J.arena = P.arena, J.arena_cap = P.arena_cap;
 	J.rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
 	int end_state[3];
-	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state);
+	__shared__ long long rtw[TB_ROWWIN];
+	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state, rtw);
 	if (threadIdx.x == 0) {
 		P.outs[pi].end_s = end_state[0], P.outs[pi].end_i = end_state[1], P.outs[pi].end_k = end_state[2];
 		P.outs[pi].n_cigar = n_cigar;
