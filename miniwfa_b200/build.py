@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 C_SOURCES = ["miniwfa.c", "kalloc.c", "mwf-dbg.c", "mwf_chain.c"]
 CU_SOURCES = ["wfa_engine.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-I", INC]
+              "-Xcompiler", "-fPIC", "-I", INC] + os.environ.get("MWF_B200_NVCC_EXTRA", "").split()  # (development builds: -DMWF_PHASE_PROF)
 CC_FLAGS = ["-O2", "-g", "-std=gnu99", "-fPIC", "-Wall", "-I", INC]
 
 

@@ -1028,8 +1028,7 @@ struct mwf_b200_batch {
 	TileCtl *d_tctl;
 	int32_t *d_state, *d_alive;
 	int2 *d_items;
-	int2 *d_qitems;        /* persistent scheduling: the work queue (payloads, sequence words) */
-	unsigned int *d_qseq;
+	unsigned long long *d_qitems; /* persistent scheduling: the work queue, one 64-bit word per entry (q_word) */
 	unsigned int q_mask;
 	bool persist;
 	int seg_K;             /* traceback segments recomputed at once (virtual slots: seg_K x wave_pairs) */
@@ -1106,9 +1105,9 @@ static void alloc_streaming(mwf_b200_batch_t *b)
 /* give the tile engine's workspaces back (the low-memory pass did not fit the arena: the streaming kernels take over) */
 static void free_tile(mwf_b200_batch_t *b)
 {
-	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_qitems); ws_free(b->d_qseq); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_qitems); ws_free(b->d_tmisc); ws_free(b->d_nseg);
 	ws_free(b->d_rowtab); ws_free(b->d_arena); ws_free(b->d_seg);
-	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->d_tmisc = 0, b->d_nseg = 0, b->d_rowtab = 0, b->d_arena = 0, b->d_seg = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_tmisc = 0, b->d_nseg = 0, b->d_rowtab = 0, b->d_arena = 0, b->d_seg = 0;
 	b->arena_total = 0, b->rowtab_stride = 0;
 }
 
@@ -1243,7 +1242,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 	ws_dev(&b->d_order, sizeof(int) * std::max(1, n_pairs), b->dev);
 	ws_dev(&b->d_ctl, 64, b->dev);
 	b->d_ring = 0, b->d_ring2 = 0, b->d_arena = 0, b->d_rowtab = 0, b->d_snapoff = 0, b->d_snaphdr = 0, b->d_seg = 0, b->d_cigar = 0;
-	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->d_qseq = 0, b->q_mask = 0, b->persist = false, b->arena_deferred = false, b->s_est = 0, b->seg_K = 1, b->d_tmisc = 0, b->h_running = 0;
+	b->d_tctl = 0, b->d_state = 0, b->d_alive = 0, b->d_items = 0, b->d_qitems = 0, b->q_mask = 0, b->persist = false, b->arena_deferred = false, b->s_est = 0, b->seg_K = 1, b->d_tmisc = 0, b->h_running = 0;
 	b->arena_total = 0, b->rowtab_stride = 0, b->snap_cap = 0, b->wave_pairs = 0;
 	if (b->is_tb) ws_dev(&b->d_cigar, sizeof(uint32_t) * std::max<size_t>(1, cw), b->dev);
 	if (pref == MWF_B200_KERNEL_TILE) {
@@ -1341,8 +1340,7 @@ extern "C" mwf_b200_batch_t *mwf_b200_batch_create(const mwf_opt_t *opt, int32_t
 			size_t need = 2 * (b->items_cap + (size_t)wp + (size_t)std::max(b->geom[0].grid_p, b->geom[b->n_geom - 1].grid_p)) + 4096, cap = 1;
 			while (cap < need) cap <<= 1;
 			b->q_mask = (unsigned int)(cap - 1);
-			ws_dev(&b->d_qitems, sizeof(int2) * cap, b->dev);
-			ws_dev(&b->d_qseq, sizeof(unsigned int) * cap, b->dev);
+			ws_dev(&b->d_qitems, sizeof(unsigned long long) * cap, b->dev);
 		}
 	} else alloc_streaming(b);
 	b->kernel_ms = 0, b->launches = 0, b->h2d = 0, b->d2h = 0, b->ran = false, b->timed = false;
@@ -1435,7 +1433,8 @@ static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np, int
  * each on its own virtual slot (state, TileCtl, alive words), so that a few very long pairs keep the GPU full */
 static int tile_pass(mwf_b200_batch_t *b, const TParams *PP, int np, int seg_j = -1, bool score_kernel = false, int group = 1)
 {
-	if (b->persist) return tile_pass_persist(b, PP, np, seg_j, score_kernel, group);
+	if (b->persist && (long long)np * group < 0x3ffffe && b->pitch / 256 < 0x3ffffe) /* (slot and tile numbers are 22-bit fields of a queue word) */
+		return tile_pass_persist(b, PP, np, seg_j, score_kernel, group);
 	int err = 0;
 	const int chunk_len = std::max(1, env_int("MWF_B200_TILE_CHUNK", 8));
 	const unsigned int many = (unsigned int)env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
@@ -1496,7 +1495,7 @@ static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np_pair
 		const mwf_b200_batch::TileGeom &G = b->geom[g];
 		P.n_pairs = np, P.vmod = vmod;
 		P.geom_id = g, P.n_geom = may_switch ? 2 : 1, P.many = env_int("MWF_B200_TILE_SWITCH", 2 * b->n_sm);
-		CUDA_OK(cudaMemsetAsync(b->d_qseq, 0, sizeof(unsigned int) * ((size_t)b->q_mask + 1), b->stream));
+		CUDA_OK(cudaMemsetAsync(b->d_qitems, 0, sizeof(unsigned long long) * ((size_t)b->q_mask + 1), b->stream));
 		wfa_tile_persist_begin_kernel<<<1, 256, 0, b->stream>>>(P, G.grid_p);
 		(score_kernel ? G.pfn_score : G.pfn)<<<G.grid_p, G.NT, G.smem, b->stream>>>(P);
 		b->launches += 2;
@@ -1508,6 +1507,19 @@ static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np_pair
 		if (env_int("MWF_B200_DEBUG", 0))
 			fprintf(stderr, "[persist dbg] round %d geometry %d: running %d, err %d, head %u tail %u, stop %d -> geometry %d, tiles in flight %d\n",
 			        round, g, hr[8], hr[10], pq->head, pq->tail, pq->stop_req, pq->switch_to, pq->total_tiles);
+#ifdef MWF_PHASE_PROF
+		{
+			unsigned long long ph[16], z[16] = {0};
+			CUDA_OK(cudaMemcpyFromSymbol(ph, g_phase, sizeof(ph)));
+			CUDA_OK(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+			double tot = 0;
+			for (int k = 0; k < 16; ++k) tot += (double)ph[k];
+			static const char *nm[16] = {"take", "setup-after-issue", "load-wait", "steps", "post-commit..return", "atom-done", "plan", "-", "store:fence", "store:issue", "store:commit", "ctl-loads", "load-issue", "wait_group0", "fence.proxy", "-"};
+			fprintf(stderr, "[phase] geometry %d grid %d (cycles per CTA %.3g):", g, G.grid_p, tot / G.grid_p);
+			for (int k = 0; k < 16; ++k) if (ph[k]) fprintf(stderr, " %s %.1f%%", nm[k], 100 * ph[k] / tot);
+			fprintf(stderr, "\n");
+		}
+#endif
 		if (hr[8] == 0) return hr[10]; /* n_running, err */
 		if (!may_switch || !pq->stop_req) die("internal error: the persistent tile kernel retired with pairs still running");
 		g = pq->switch_to;
@@ -1523,7 +1535,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	P.order = b->d_order, P.pairs = b->d_pairs, P.outs = b->d_outs, P.seq = b->d_seq, P.seqp = b->d_seqp, P.seqp2 = b->d_seqp2, P.packed = b->d_packed, P.cigar = b->d_cigar;
 	P.ctl = b->d_tctl, P.state = b->d_state, P.alive = b->d_alive;
 	P.pitch = b->pitch, P.R = b->tR;
-	P.pq = (PersistCtl*)(b->d_tmisc + 96), P.q_items = b->d_qitems, P.q_seq = b->d_qseq, P.q_mask = b->q_mask;
+	P.pq = (PersistCtl*)(b->d_tmisc + 96), P.q_items = b->d_qitems, P.q_mask = b->q_mask, P.q_bits = (unsigned int)__builtin_popcount(b->q_mask);
 	P.items = b->d_items, P.cnt = (TileCounters*)b->d_tmisc, P.n_running = (int*)(b->d_tmisc + 32), P.err = (int*)(b->d_tmisc + 40);
 	P.arena = b->d_arena, P.arena_cap = b->arena_total, P.arena_used = (unsigned long long*)(b->d_tmisc + 64);
 	P.rowtab = b->d_rowtab, P.rowtab_stride = b->rowtab_stride;
@@ -1628,7 +1640,7 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 			while (K > 1 && (double)K * wp * per_slot > 0.1 * (double)free_b) --K;
 			if (K > 1) {
 				b->seg_K = K;
-				ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_tctl); ws_free(b->d_qitems); ws_free(b->d_qseq);
+				ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_tctl); ws_free(b->d_qitems);
 				if (ws_dev(&b->d_state, (size_t)K * wp * 2 * b->tR * b->pitch * 4, b->dev))
 					CUDA_OK(cudaMemsetAsync(b->d_state, 0xC0, (size_t)K * wp * 2 * b->tR * b->pitch * 4, b->stream));
 				ws_dev(&b->d_alive, (size_t)K * wp * b->pitch * 4, b->dev);
@@ -1636,8 +1648,7 @@ static void run_tile_segmented(mwf_b200_batch_t *b)
 				size_t need_q = 2 * ((size_t)K * b->items_cap + (size_t)K * wp + (size_t)std::max(b->geom[0].grid_p, b->geom[b->n_geom - 1].grid_p)) + 4096, cap = 1;
 				while (cap < need_q) cap <<= 1;
 				b->q_mask = (unsigned int)(cap - 1);
-				ws_dev(&b->d_qitems, sizeof(int2) * cap, b->dev);
-				ws_dev(&b->d_qseq, sizeof(unsigned int) * cap, b->dev);
+				ws_dev(&b->d_qitems, sizeof(unsigned long long) * cap, b->dev);
 				b->arena_total = std::min(half, ((long long)K * need + 255) & ~255LL);
 			}
 		}
@@ -1934,7 +1945,7 @@ extern "C" void mwf_b200_batch_destroy(mwf_b200_batch_t *b)
 	ws_free(b->d_seq); ws_free(b->h_seq); ws_free(b->d_pairs); ws_free(b->d_outs); ws_free(b->h_outs);
 	ws_free(b->d_order); ws_free(b->d_ctl); ws_free(b->d_ring); ws_free(b->d_ring2); ws_free(b->d_arena);
 	ws_free(b->d_rowtab); ws_free(b->d_snapoff); ws_free(b->d_snaphdr); ws_free(b->d_seg); ws_free(b->d_cigar);
-	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_qitems); ws_free(b->d_qseq); ws_free(b->d_tmisc); ws_free(b->d_nseg);
+	ws_free(b->d_tctl); ws_free(b->d_state); ws_free(b->d_alive); ws_free(b->d_items); ws_free(b->d_qitems); ws_free(b->d_tmisc); ws_free(b->d_nseg);
 	ws_free(b->d_seqp); ws_free(b->d_seqp2); ws_free(b->d_packed);
 	ws_free(b->d_snap); ws_free(b->d_snapdir); ws_free(b->d_nsnap); ws_free(b->d_sstop); ws_free(b->h_nsnap); ws_free(b->d_trace);
 	if (b->h_running) { ws_free(b->h_running); cudaEventDestroy(b->evc[0]); cudaEventDestroy(b->evc[1]); }

@@ -55,7 +55,7 @@ struct TileCounters { unsigned int n_items, next; };
 
 /* persistent scheduling (wfa_tile_persist_kernel): one queue of work items per pass, fed by the planner that runs inside the
  * tile kernel.  An item is (pair, tile) -- or (pair, -1): plan the pair's next block -- or (-1, .): retire.  Consumers take
- * tickets from `head`; the item of ticket t is published by storing t + 1 into q_seq[t & mask] after its payload. */
+ * tickets from `head`; the item of ticket t is published by storing its word (q_word) into q_items[t & mask]. */
 struct PersistCtl {
 	unsigned int head, tail;
 	int n_inflight;    /* pairs with a block in flight (or a plan item queued); 0 => the retire items go out */
@@ -104,9 +104,8 @@ struct TParams {
 	int fast;                  /* interior tiles of the 4-cells-per-thread geometry keep the gap rows in registers (tile_cells_fast) */
 	/* persistent scheduling */
 	PersistCtl *pq;
-	int2 *q_items;
-	unsigned int *q_seq;
-	unsigned int q_mask;
+	unsigned long long *q_items; /* [q_mask + 1] entries, zeroed before a pass (q_word) */
+	unsigned int q_mask, q_bits;  /* q_mask + 1 = 1 << q_bits */
 	int vmod;                  /* > 0: slot v stands for pair slot v % vmod (several traceback segments of a pair recomputed at once) */
 	int geom_id, n_geom, many; /* this launch's geometry (0 latency, 1 throughput); switch above `many` / below many / 2 tiles in flight */
 	/* segmented traceback */
@@ -221,28 +220,37 @@ __device__ __forceinline__ void st_volatile_u32(unsigned int *p, unsigned int v)
 {
 	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-/* publish item `ticket`: payload, fence, then the sequence word the consumer spins on */
-__device__ __forceinline__ void q_publish(const TParams &P, unsigned int ticket, int pair, int tile)
+/* A queue entry is ONE 64-bit word: lap tag (20 bits, never 0) | slot + 1 (22 bits) | tile + 1 (22 bits), so that publishing is a
+ * single store and taking an item a single load -- no payload / sequence-word pair and no second round trip to L2. */
+__device__ __forceinline__ unsigned long long q_word(const TParams &P, unsigned int ticket, int slot, int tile)
 {
-	const unsigned int i = ticket & P.q_mask;
-	__stcg(P.q_items + i, make_int2(pair, tile));
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(P.q_seq + i), "r"(ticket + 1u) : "memory"); /* (a release, not __threadfence(): that one also drops the SM's L1) */
+	const unsigned long long tag = (ticket >> P.q_bits) % 0xfffffu + 1u;
+	return tag << 44 | (unsigned long long)(unsigned int)(slot + 1) << 22 | (unsigned long long)(unsigned int)(tile + 1);
+}
+/* publish item `ticket` (a release, not __threadfence(): that one also drops the SM's L1) */
+__device__ __forceinline__ void q_publish(const TParams &P, unsigned int ticket, int slot, int tile)
+{
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(P.q_items + (ticket & P.q_mask)), "l"(q_word(P, ticket, slot, tile)) : "memory");
 }
 
-/* take a ticket and wait for its item (one thread per CTA).  No acquire fence: it would drop the L1 lines of all four CTAs of the
- * SM (the sequence windows) on every item.  The payload load is issued only after the sequence word has been seen, the producer
- * released it after the payload, and everything other SMs write inside this kernel is read past L1 (ld.cg, bulk copies).
- * Not inlined: the tile kernel sits at its register limit. */
-__device__ __noinline__ int2 q_take(const TParams &P)
+/* wait for the item of a ticket taken from `head` (one thread per CTA).  No acquire fence: it would drop the L1 lines of all four
+ * CTAs of the SM (the sequence windows) on every item; the producer released the word after everything the item refers to, and
+ * everything other SMs write inside this kernel is read past L1 (ld.cg, bulk copies).  Not inlined: the tile kernel sits at its
+ * register limit. */
+__device__ __noinline__ int2 q_take(const TParams &P, const unsigned int ticket)
 {
-	const unsigned int ticket = atomicAdd(&P.pq->head, 1u), i = ticket & P.q_mask;
+	const unsigned long long *q = P.q_items + (ticket & P.q_mask);
+	const unsigned int tag = (ticket >> P.q_bits) % 0xfffffu + 1u;
 	unsigned int ns = 32, spins = 0;
-	while (ld_volatile_u32(P.q_seq + i) != ticket + 1u) {
+	unsigned long long w;
+	for (;;) {
+		asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(q) : "memory");
+		if ((unsigned int)(w >> 44) == tag) break;
 		__nanosleep(ns);
 		if (ns < 256) ns <<= 1;
 		if (++spins == 0x30000000u) __trap(); /* minutes without an item: a lost hand-over must end as a launch failure, not as a device that hangs for good */
 	}
-	return __ldcg(P.q_items + i);
+	return make_int2((int)((unsigned int)(w >> 22) & 0x3fffffu) - 1, (int)((unsigned int)w & 0x3fffffu) - 1);
 }
 
 /* The planner of one pair: replay the block that has just finished, trim, cut the next block and hand out its tiles.
@@ -406,16 +414,16 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 	}
 	} /* thread 0 */
 	__syncthreads();
-	if (PERSIST) { /* the block's tiles: every payload of this thread first, then ONE release (a MEMBAR each would cost a large pair
-	                * with thousands of tiles per block tens of microseconds in which the whole GPU waits), then the sequence words */
+	if (PERSIST) { /* the block's tiles: ONE release per thread, the rest of its words relaxed (a MEMBAR each would cost a large pair
+	                * with thousands of tiles per block tens of microseconds in which the whole GPU waits) */
 		const unsigned int base = (unsigned int)sh_emit[0];
 		const int n_emit = sh_emit[1];
-		for (int j = threadIdx.x; j < n_emit; j += blockDim.x) __stcg(P.q_items + ((base + j) & P.q_mask), make_int2(slot, j));
 		bool first = true;
 		for (int j = threadIdx.x; j < n_emit; j += blockDim.x) {
-			unsigned int *sq = P.q_seq + ((base + j) & P.q_mask);
-			if (first) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(sq), "r"(base + j + 1u) : "memory");
-			else asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(sq), "r"(base + j + 1u) : "memory"); /* (after the release in program order) */
+			unsigned long long *q = P.q_items + ((base + j) & P.q_mask);
+			const unsigned long long w = q_word(P, base + j, slot, j);
+			if (first) asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(q), "l"(w) : "memory");
+			else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(q), "l"(w) : "memory"); /* (after the release in program order) */
 			first = false;
 		}
 	} else {
@@ -1138,13 +1146,25 @@ __device__ __forceinline__ int tile_fast2_block(const Fast2Ctx<CPT> &c, const St
 /* the persistent CTA state of the tile kernels: shared-memory layout and the phases of the two mbarriers */
 struct TileSmem {
 	int32_t *rows;        /* [R][W] */
-	int *sc;              /* [0..2] flags, [3..5] item */
+	int *sc;              /* [0..2] flags, [3..7] item, [8..11] the two mbarriers, [12..13] ticket taken ahead */
 	uint64_t *bar, *stepbar;
 	StepTab *steptab;     /* [max(T, 2)] row offsets of the steps of the block in flight */
 	uint32_t xch;         /* [2][TILE_MAX_WARPS + 2] records of 16 bytes: gap cells across warp boundaries */
 	uint32_t sb;          /* shared address of this thread's cells in row 0 */
 	uint32_t phase, step_phase;
 };
+
+#ifdef MWF_PHASE_PROF /* development build only: clock cycles of thread 0 per phase of the persistent kernel, summed over CTAs */
+__device__ unsigned long long g_phase[16];
+#define PH_DECL __shared__ long long ph_acc[16]; __shared__ long long ph_last; long long *const ph_p = ph_acc, *const ph_l = &ph_last;
+#define PH(k) do { if (threadIdx.x == 0) { const long long now_ = clock64(); ph_p[k] += now_ - *ph_l; *ph_l = now_; } } while (0)
+#define PH_ARGS , long long *ph_p, long long *ph_l
+#define PH_PASS , ph_p, ph_l
+#else
+#define PH(k) do {} while (0)
+#define PH_ARGS
+#define PH_PASS
+#endif
 
 template<int CPT>
 __device__ __forceinline__ void tile_smem_setup(const TParams &P, int32_t *smem_tile, TileSmem &S)
@@ -1157,13 +1177,13 @@ __device__ __forceinline__ void tile_smem_setup(const TParams &P, int32_t *smem_
 	S.xch = smem_u32(S.steptab + max(P.T, 2));
 	S.sb = smem_u32(S.rows) + 4 * CPT * tid;
 	S.phase = 0, S.step_phase = 0;
-	if (tid == 0) { mbar_init(S.bar, 1); mbar_init(S.stepbar, blockDim.x >> 5); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	if (tid == 0) { S.sc[12] = 0; mbar_init(S.bar, 1); mbar_init(S.stepbar, blockDim.x >> 5); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 }
 
 /* One work item: tile `tile` of the block in flight of pair `slot` -- load, Tb fused next+extend steps, store.  On return the
  * bulk stores of the tile are committed (not yet complete); returns the number of tiles of the block. */
 template<int MODE, int CPT>
-__device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const int slot, const int tile, bool &wrote_alive)
+__device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const int slot, const int tile, bool &wrote_alive PH_ARGS)
 {
 	const int W = P.W, R = P.R, HL = P.HL, pitch = P.pitch;
 	int32_t *rows = S.rows;
@@ -1189,6 +1209,7 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	int32_t *st_in = P.state + ((size_t)slot * 2 + cur) * R * pitch;
 	int32_t *st_out = P.state + ((size_t)slot * 2 + (cur ^ 1)) * R * pitch;
 	/* ---- load the tile: R rows of W int32, one bulk copy per row ---- */
+	PH(11);
 	if (tid < 32) {
 		fence_async_smem();
 		if (tid == 0) mbar_expect_tx(bar, (uint32_t)(R * W * 4));
@@ -1196,6 +1217,7 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 		for (int r = tid; r < R; r += 32)
 			bulk_g2s(rows + (size_t)r * W, st_in + (size_t)r * pitch + idx0, (uint32_t)(W * 4), bar);
 	}
+	PH(12);
 	if (tid < 3) sc[tid] = 0;
 	if (P.fast && tid < max(Tb, 2)) { /* step tid+1 of the block works on score s0 + tid + 1 */
 		const int s = s0 + tid + 1;
@@ -1229,9 +1251,11 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	const int t_alive = bnd - n - s0; /* steps t > t_alive feed wf_stripe_shrink (:144-171) */
 	int alive_bits = 0;
 	int hs = s0 % n, e1s = s0 % d1, e2s = s0 % d2;
+	PH(1);
 	mbar_wait(bar, phase);
 	phase ^= 1;
 	__syncthreads();
+	PH(2);
 	const long long snap_off = __ldcg(&ctl->snap_off);
 	if (snap_off >= 0) { /* snapshot for the segmented traceback: the state at score s0, useful columns of every row */
 		if (tid < 32) {
@@ -1340,12 +1364,16 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 			if ((fl & FL_DONE) && tid == 0 && __ldcg(&ctl->done_t) == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
 		}
 	}
+	PH(3);
 	/* ---- store the useful columns of every row into the other state buffer ---- */
 	if (tid < 32) {
 		fence_async_smem();
+		PH(8);
 		for (int r = tid; r < R; r += 32)
 			bulk_s2g(st_out + (size_t)r * pitch + ustart, rows + (size_t)r * W + HL, (uint32_t)(ulen * 4));
+		PH(9);
 		bulk_commit();
+		PH(10);
 	}
 	if (tid == 0) {
 		if (left_edge) ctl->fin_lo = wflo_c;
@@ -1380,7 +1408,10 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 		if (item >= n_items) break;
 		const int2 it2 = P.items[item];
 		bool wrote_alive;
-		tile_item<MODE, CPT>(P, S, it2.x, it2.y, wrote_alive);
+#ifdef MWF_PHASE_PROF
+		PH_DECL
+#endif
+		tile_item<MODE, CPT>(P, S, it2.x, it2.y, wrote_alive PH_PASS);
 		if (tid < 32) bulk_wait_read(); /* the rows may be overwritten by the next item's load */
 	}
 	if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* stores complete before the CTA retires */
@@ -1403,21 +1434,31 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 	TileSmem S;
 	tile_smem_setup<CPT>(P, smem_tile, S);
 	const int tid = threadIdx.x;
+#ifdef MWF_PHASE_PROF
+	PH_DECL
+	if (tid == 0) { for (int k = 0; k < 16; ++k) ph_acc[k] = 0; ph_last = clock64(); }
+#endif
 	for (;;) {
 		__syncthreads();
-		if (tid == 0) {
-			const int2 v = q_take(P);
-			S.sc[3] = v.x, S.sc[4] = v.y, S.sc[5] = 0;
+		if (tid == 0) { /* (the ticket was taken while the previous tile's stores drained, when there was one) */
+			const unsigned int ticket = S.sc[12] ? (unsigned int)S.sc[13] : atomicAdd(&P.pq->head, 1u);
+			const int2 v = q_take(P, ticket);
+			S.sc[3] = v.x, S.sc[4] = v.y, S.sc[5] = 0, S.sc[12] = 0;
 		}
 		__syncthreads();
 		const int slot = S.sc[3], tile = S.sc[4];
+		PH(0);
 		if (slot < 0) break;
 		bool plan = tile < 0;
 		if (!plan) {
 			asm volatile("fence.proxy.async;" ::: "memory"); /* the state rows were written through the async proxy of other SMs */
 			bool wrote_alive;
-			const int n_tiles = tile_item<MODE, CPT>(P, S, slot, tile, wrote_alive);
-			if (tid < 32) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); asm volatile("fence.proxy.async;" ::: "memory"); }
+			const int n_tiles = tile_item<MODE, CPT>(P, S, slot, tile, wrote_alive PH_PASS);
+			PH(4);
+			unsigned int next_ticket = 0;
+			if (tid == 0) next_ticket = atomicAdd(&P.pq->head, 1u); /* its round trip overlaps the waits below; the item is awaited only after this CTA's duties (count, plan) */
+			if (tid < 32) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); PH(13); asm volatile("fence.proxy.async;" ::: "memory"); }
+			PH(14);
 			if (wrote_alive) /* one block in eight: every thread has stored alive words.  A release on a scratch word orders them
 			                  * (MEMBAR.ALL.GPU) without the L1 invalidation __threadfence() would add */
 				asm volatile("red.release.gpu.global.add.s32 [%0], 0;" :: "l"(&P.pq->scratch) : "memory");
@@ -1426,9 +1467,11 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				int prev;
 				asm volatile("atom.add.release.gpu.global.s32 %0, [%1], 1;" : "=r"(prev) : "l"(&P.ctl[slot].tiles_done) : "memory");
 				S.sc[5] = prev == n_tiles - 1;
+				S.sc[12] = 1, S.sc[13] = (int)next_ticket;
 			}
 			__syncthreads();
 			plan = S.sc[5] != 0;
+			PH(5);
 		}
 		if (plan) {
 			__syncthreads();
@@ -1440,8 +1483,12 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 				__syncthreads();
 				for (unsigned int j = tid; j < gridDim.x; j += blockDim.x) q_publish(P, (unsigned int)S.sc[7] + j, -1, -1);
 			}
+			PH(6);
 		}
 	}
+#ifdef MWF_PHASE_PROF
+	if (tid == 0) for (int k = 0; k < 16; ++k) atomicAdd(&g_phase[k], (unsigned long long)ph_acc[k]);
+#endif
 }
 
 /* start of a persistent pass (or of its continuation in the other tile geometry): one plan item per running pair */
