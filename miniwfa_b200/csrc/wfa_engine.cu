@@ -1513,10 +1513,11 @@ static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np_pair
 			CUDA_OK(cudaMemcpyFromSymbol(ph, g_phase, sizeof(ph)));
 			CUDA_OK(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
 			double tot = 0;
-			for (int k = 0; k < 16; ++k) tot += (double)ph[k];
-			static const char *nm[16] = {"take", "setup-after-issue", "load-wait", "steps", "post-commit..return", "atom-done", "plan", "-", "store:fence", "store:issue", "store:commit", "ctl-loads", "load-issue", "wait_group0", "fence.proxy", "-"};
+			for (int k = 0; k < 14; ++k) tot += (double)ph[k];
+			static const char *nm[16] = {"take", "setup-after-issue", "load-wait", "steps", "post-commit..return", "atom-done", "plan", "steps(special tiles)", "store:fence", "store:issue", "store:commit", "ctl-loads", "load-issue", "wait_group0+fence", "#interior", "#special"};
 			fprintf(stderr, "[phase] geometry %d grid %d (cycles per CTA %.3g):", g, G.grid_p, tot / G.grid_p);
-			for (int k = 0; k < 16; ++k) if (ph[k]) fprintf(stderr, " %s %.1f%%", nm[k], 100 * ph[k] / tot);
+			for (int k = 0; k < 14; ++k) if (ph[k]) fprintf(stderr, " %s %.1f%%", nm[k], 100 * ph[k] / tot);
+			fprintf(stderr, " | tiles: interior %llu special %llu", ph[14], ph[15]);
 			fprintf(stderr, "\n");
 		}
 #endif

@@ -1364,7 +1364,9 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 			if ((fl & FL_DONE) && tid == 0 && __ldcg(&ctl->done_t) == 0x7fffffff) { ctl->done_t = t; ctl->done_last = fl >> FL_LAST_SHIFT; }
 		}
 	}
-	PH(3);
+#ifdef MWF_PHASE_PROF
+	if (special) { PH(7); if (threadIdx.x == 0) ph_p[15] += 1; } else { PH(3); if (threadIdx.x == 0) ph_p[14] += 1; }
+#endif
 	/* ---- store the useful columns of every row into the other state buffer ---- */
 	if (tid < 32) {
 		fence_async_smem();
@@ -1457,8 +1459,8 @@ __global__ void __launch_bounds__(TILE_MAX_THREADS(CPT), TILE_MIN_CTAS(CPT)) wfa
 			PH(4);
 			unsigned int next_ticket = 0;
 			if (tid == 0) next_ticket = atomicAdd(&P.pq->head, 1u); /* its round trip overlaps the waits below; the item is awaited only after this CTA's duties (count, plan) */
-			if (tid < 32) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); PH(13); asm volatile("fence.proxy.async;" ::: "memory"); }
-			PH(14);
+			if (tid < 32) { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); asm volatile("fence.proxy.async;" ::: "memory"); }
+			PH(13);
 			if (wrote_alive) /* one block in eight: every thread has stored alive words.  A release on a scratch word orders them
 			                  * (MEMBAR.ALL.GPU) without the L1 invalidation __threadfence() would add */
 				asm volatile("red.release.gpu.global.add.s32 [%0], 0;" :: "l"(&P.pq->scratch) : "memory");
