@@ -1505,8 +1505,12 @@ static int tile_pass_persist(mwf_b200_batch_t *b, const TParams *PP, int np_pair
 		CUDA_OK(cudaStreamSynchronize(b->stream));
 		const PersistCtl *pq = (const PersistCtl*)(hr + 24);
 		if (env_int("MWF_B200_DEBUG", 0))
-			fprintf(stderr, "[persist dbg] round %d geometry %d: running %d, err %d, head %u tail %u, stop %d -> geometry %d, tiles in flight %d\n",
-			        round, g, hr[8], hr[10], pq->head, pq->tail, pq->stop_req, pq->switch_to, pq->total_tiles);
+		{
+			TileCtl h;
+			CUDA_OK(cudaMemcpy(&h, b->d_tctl, sizeof(h), cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[persist dbg] round %d geometry %d: running %d, err %d, head %u tail %u, stop %d -> geometry %d, tiles in flight %d; pair 0: s %d band [%d, %d] last shrink at %d\n",
+			        round, g, hr[8], hr[10], pq->head, pq->tail, pq->stop_req, pq->switch_to, pq->total_tiles, h.s, h.wflo, h.wfhi, h.shrink_s);
+		}
 #ifdef MWF_PHASE_PROF
 		{
 			unsigned long long ph[16], z[16] = {0};
@@ -1544,6 +1548,7 @@ static void tile_params(mwf_b200_batch_t *b, TParams *PP)
 	/* (the fast path addresses the sequences by 32-bit bit positions inside the sequence buffer) */
 	P.fast = env_int("MWF_B200_TILE_FAST", 2) * (int)(b->pen.e1 <= 2 && b->pen.e2 <= 2 && (long long)b->seq_bytes < (1LL << 28));
 	if (P.fast >= 2 && !b->d_seqp2) P.fast = 1;
+	P.fast_edge = env_int("MWF_B200_TILE_FASTEDGE", 1);
 	P.seg = b->d_seg, P.n_seg = b->d_nseg, P.seg_stride = 2 * b->snap_cap, P.step = b->opt.step;
 	for (int g = 0; g < 2; ++g) { /* per geometry: tile width, block length, row tables */
 		const mwf_b200_batch::TileGeom &G = b->geom[g < b->n_geom ? g : 0];

@@ -40,14 +40,16 @@ enum { TS_RUN = 0, TS_DONE = 1, TS_STOPPED = 2, TS_ARENA = 3, TS_SHRINK = 4, TS_
 
 struct TileCtl { /* per pair, lives in HBM for the whole run */
 	int status, s, wflo, wfhi, cur, last, sid, copied;
-	int tiles_done, pad0_; /* persistent scheduling: tiles of the block in flight that have finished */
+	int tiles_done;        /* persistent scheduling: tiles of the block in flight that have finished */
+	int shrink_s;          /* score of the last trim / band collapse that took diagonals away (slices older than that still hold them) */
 	long long n_iter;
 	/* the block in flight */
 	int Tb, A4, total4, n_tiles;
 	int done_t, done_last, fin_lo, fin_hi;
 	long long row_base, row_size; /* traceback rows of the block: byte (row t, index i) at row_base + (t-1)*row_size + i */
 	long long snap_off;           /* >= 0: the tiles of this block also save the state they load (a snapshot at score s) */
-	int snap_rowsize, snap_pad;
+	int snap_rowsize;
+	int nat_ok;            /* every slice the block in flight reads is newer than shrink_s: nothing lies outside the band (tile_fast2_block<.., true>) */
 	int lo_log[TILE_TMAX], hi_log[TILE_TMAX];
 };
 
@@ -102,6 +104,7 @@ struct TParams {
 	int seg_stride, seg_use, step; /* seg_use: this pass collapses the band at the checkpoints (pass 2, miniwfa.c:413-416) */
 	int s_limit;               /* no alignment of the batch can cost more (all-gap bound): a guard against endless runs */
 	int fast;                  /* interior tiles of the 4-cells-per-thread geometry keep the gap rows in registers (tile_cells_fast) */
+	int fast_edge;             /* tiles at the band's edges / on the terminal diagonal run the register-resident step too (tile_fast2_block<.., true>) */
 	/* persistent scheduling */
 	PersistCtl *pq;
 	unsigned long long *q_items; /* [q_mask + 1] entries, zeroed before a pass (q_word) */
@@ -193,7 +196,7 @@ __global__ void wfa_tile_init_kernel(const TParams P, int slot0)
 		const int k = extend_run(T, Q, -1, 0, min(pd.tl - 1, pd.ql - 1));
 		st[doff] = k; /* H of score 0 lives in slot 0 */
 		TileCtl *c = P.ctl + slot;
-		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = 0;
+		c->s = 0, c->wflo = c->wfhi = 0, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = 0, c->shrink_s = -0x10000, c->nat_ok = 0;
 		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1, c->tiles_done = 0;
 		c->status = (k == pd.tl - 1 && k == pd.ql - 1) ? TS_DONE : TS_RUN;
 		if (c->status == TS_DONE) {
@@ -315,7 +318,10 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 			__syncthreads();
 			const int nl = sh[2], nh = sh[3];
 			if (nl > wfhi || nh < nl) status = TS_SHRINK; /* the reference asserts (:157, :169) */
-			else wflo = nl, wfhi = nh;
+			else {
+				if (threadIdx.x == 0 && (nl != wflo || nh != wfhi)) c->shrink_s = s;
+				wflo = nl, wfhi = nh;
+			}
 		}
 	}
 	if (threadIdx.x == 0) sh_emit[1] = 0, sh_emit[3] = 0;
@@ -339,7 +345,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 			                                                  that follow store only their own columns, but still read the wide slices */
 			else {
 				wflo = wfhi = seg[2 * sid + 1];
-				++sid, c->copied = 0;
+				++sid, c->copied = 0, c->shrink_s = s;
 			}
 		}
 		Tb = min(P.T, ((s | 0xff) + 1) - s);
@@ -381,6 +387,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 			c->wflo = wflo, c->wfhi = wfhi, c->sid = sid;
 			c->Tb = Tb, c->A4 = A4, c->total4 = total4, c->n_tiles = n_tiles;
 			c->done_t = 0x7fffffff, c->done_last = 0, c->tiles_done = 0;
+			c->nat_ok = s - CL(shrink_s) >= n;
 			if (PERSIST) {
 				sh_emit[0] = (int)atomicAdd(&P.pq->tail, (unsigned int)n_tiles), sh_emit[1] = n_tiles;
 				const int tot = atomicAdd(&P.pq->total_tiles, n_tiles - old_tiles) + n_tiles - old_tiles;
@@ -969,10 +976,11 @@ template<int CPT> struct Fast2Ctx {
 /* LCB = log2(bits per code): 1 for two-bit codes (DNA), 2 for four-bit codes (DNA with N, soft-masked, IUPAC).  CPT = 4 is the
  * throughput geometry (cells 1 and 2 of a thread need nothing from other warps and go before the step barrier's wait); CPT = 2
  * and 1 put more warps on a tile, for single large pairs. */
-template<int MODE, int CPT, int LCB>
+template<int MODE, int CPT, int LCB, bool EDGE>
 __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const int4 qh, const uint32_t xoff_r, const uint32_t xoff_w, const SeqView &sv,
                                                  int (&pe1)[CPT], int (&pf1)[CPT], const int (&oe1)[CPT], const int (&of1)[CPT], int (&pe2)[CPT], int (&pf2)[CPT],
-                                                 uint64_t *stepbar, bool wait, uint32_t parity, int (&Hn)[CPT], uint32_t &tb_out)
+                                                 uint64_t *stepbar, bool wait, uint32_t parity, int (&Hn)[CPT], uint32_t &tb_out,
+                                                 const int jfin, const int tlm1, uint32_t &inval_bits, int &done_z)
 {
 	constexpr uint32_t CB = 1u << LCB;
 	int ho1[CPT], ho2[CPT], hx[CPT];
@@ -1026,6 +1034,7 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const i
 		const uint2 tv = __ldg(c.seqw + (tpb >> 5)), qv = __ldg(c.seqw + (qpb >> 5)); \
 		tz[j] = ctz32_sat(__funnelshift_r(tv.x, tv.y, tpb) ^ __funnelshift_r(qv.x, qv.y, qpb)); \
 		lim[j] = c.kend[j] - (int)tpb; \
+		if (EDGE && LCB > 1 && H < -1) lim[j] = 0; /* (cells outside the band: 4 H wraps to a position inside T; interior tiles hold no such cell) */ \
 	} while (0)
 	if (CPT == 4) { FAST2_CELL(1); FAST2_CELL(2); }
 	if (wait) mbar_wait(stepbar, parity); /* every warp has finished the previous score */
@@ -1072,6 +1081,18 @@ __device__ __forceinline__ void tile_cells_fast2(const Fast2Ctx<CPT> &c, const i
 	}
 	stsv<CPT>(c.sb + qh.w, Hn);
 	tb_out = tbw;
+	if (EDGE) { /* tiles at the band's edges / holding the terminal diagonal (tile_fast2_block) */
+		uint32_t iv = 0; /* bit j: cell j holds no value (H is the largest of the five, so H < -1 says it for all of them: the edge rule, :325-326) */
+#pragma unroll
+		for (int j = CPT - 1; j >= 0; --j) iv = __funnelshift_l((uint32_t)(Hn[j] + 1), iv, 1);
+		inval_bits = iv;
+		done_z = -1;
+		if (jfin >= 0) { /* the end of both sequences (:405-409); the state that got there when no match run was added (wf_traceback's start) */
+#pragma unroll
+			for (int j = 0; j < CPT; ++j)
+				if (j == jfin && Hn[j] == tlm1) done_z = (MODE != MODE_SCORE && Hn[j] == h0[j]) ? (int)(tbw >> (8 * j) & 7u) : 0;
+		}
+	}
 }
 
 /* the cells of a thread that wf_stripe_shrink keeps: any of the five values on the matrix.  H is the largest of the five, so the
@@ -1093,14 +1114,22 @@ __device__ __forceinline__ int alive_cells_h(int d0, int tl, int ql, const int (
 	return bits;
 }
 
-template<int MODE, int CPT, int LCB>
+/* EDGE = true: the same steps for a tile at an edge of the band and / or holding the terminal diagonal.  The caller has set every
+ * cell outside the band [wflo0, wfhi0] of the block's first score to NEG_INF in all rows of the tile (what the reference's pads hold),
+ * and no diagonal of the tile lies outside [-tl, ql].  Then the recurrence itself grows the band the way the reference does: the only
+ * cell outside the band that can get a value in a step is the one next to it (its sources are cells of the band), and the reference
+ * takes exactly that cell in when it holds a value (:325-326, :417-418).  A cell that gets its first value says so with one bit per step
+ * and side in sc[12..15]; the terminal diagonal reports the first step in which it reaches the end of both sequences. */
+template<int MODE, int CPT, int LCB, bool EDGE>
 __device__ __forceinline__ int tile_fast2_block(const Fast2Ctx<CPT> &c, const StepTab *tab, const SeqView &sv, uint32_t f1off, uint32_t f2off, int d0, int Tb, int t_alive,
-                                                int tl, int ql, bool useful, uint8_t *tbp, long long tb_pitch, uint64_t *stepbar, uint32_t &step_phase)
+                                                int tl, int ql, bool useful, uint8_t *tbp, long long tb_pitch, uint64_t *stepbar, uint32_t &step_phase,
+                                                const uint32_t outl, const uint32_t outr, const int jfin, int *sc, int &done_t, int &done_last)
 {
 	const int lane = threadIdx.x & 31;
 	int e1a[CPT], f1a[CPT], e1b[CPT], f1b[CPT], e2a[CPT], f2a[CPT], Hn[CPT];
 	int alive_bits = 0;
-	uint32_t tbw;
+	uint32_t tbw, ever = 0, iv = 0;
+	int dz = -1;
 	ldsv<CPT>(c.sb + tab[0].e.x, e1a); ldsv<CPT>(c.sb + tab[0].e.x + f1off, f1a); /* E1 / F1 of scores s0 - 1 and s0 */
 	ldsv<CPT>(c.sb + tab[1].e.x, e1b); ldsv<CPT>(c.sb + tab[1].e.x + f1off, f1b);
 	ldsv<CPT>(c.sb + tab[0].e.y, e2a); ldsv<CPT>(c.sb + tab[0].e.y + f2off, f2a); /* E2 / F2 of score s0 */
@@ -1110,10 +1139,19 @@ __device__ __forceinline__ int tile_fast2_block(const Fast2Ctx<CPT> &c, const St
 	}
 	__syncthreads();
 #define FAST2_STEP(X1, Y1, O1, P1, XR, XW) do { \
-		tile_cells_fast2<MODE, CPT, LCB>(c, tab[t - 1].h, XR, XW, sv, X1, Y1, O1, P1, e2a, f2a, stepbar, t > 1, step_phase & 1, Hn, tbw); \
+		tile_cells_fast2<MODE, CPT, LCB, EDGE>(c, tab[t - 1].h, XR, XW, sv, X1, Y1, O1, P1, e2a, f2a, stepbar, t > 1, step_phase & 1, Hn, tbw, jfin, tl - 1, iv, dz); \
 		if (t > 1) ++step_phase; \
 		if (MODE == MODE_TB) { if (useful) store_tb<CPT>(tbp, tbw); tbp += tb_pitch; } \
 		if (t > t_alive) alive_bits |= alive_cells_h<CPT>(d0, tl, ql, Hn, X1, Y1, e2a, f2a); \
+		if (EDGE) { \
+			const uint32_t nw = ~iv & (outl | outr) & ~ever; \
+			if (nw) { \
+				ever |= nw; \
+				if (nw & outl) atomicOr(&sc[12 + ((t - 1) >> 5)], 1 << ((t - 1) & 31)); \
+				if (nw & outr) atomicOr(&sc[14 + ((t - 1) >> 5)], 1 << ((t - 1) & 31)); \
+			} \
+			if (dz >= 0 && done_t == 0x7fffffff) done_t = t, done_last = dz; \
+		} \
 		if (t < Tb) { __syncwarp(); if (lane == 0) step_arrive(stepbar); } \
 	} while (0)
 	int t = 1;
@@ -1271,7 +1309,9 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 	/* ---- Tb fused next+extend steps ---- */
 	CellOut<CPT> o;
 	bool stepped = false;
-	if (!special && Tb > 0 && P.fast >= 2 && code_bits != 0 && P.pen.e1 == 2 && P.pen.e2 == 1) { /* interior tile, packed codes, default gap extensions */
+	const bool fast2_ok = Tb > 0 && P.fast >= 2 && code_bits != 0 && P.pen.e1 == 2 && P.pen.e2 == 1; /* packed codes, default gap extensions */
+	const bool fast_edge = special && fast2_ok && P.fast_edge && __ldcg(&ctl->nat_ok) && idx0 - doff >= -tl && idx0 - doff + W - 1 <= ql; /* (no diagonal of the tile off the matrix) */
+	if ((!special && fast2_ok) || fast_edge) { /* the register-resident step */
 		Fast2Ctx<CPT> c;
 		const uint32_t rb = 4u * W, cb = (uint32_t)code_bits;
 		const int warp = tid >> 5;
@@ -1286,9 +1326,46 @@ __device__ __forceinline__ int tile_item(const TParams &P, TileSmem &S, const in
 #pragma unroll
 		for (int j = 0; j < CPT; ++j) c.kend[j] = (int)cb * min(tl - 1, ql - 1 - (d0 + j)) + (int)c.c1;
 		c.d0 = d0;
-		if (code_bits == 2) alive_bits = tile_fast2_block<MODE, CPT, 1>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-		else alive_bits = tile_fast2_block<MODE, CPT, 2>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase);
-		__syncthreads();
+		int done_t = 0x7fffffff, done_last = 0;
+		if (!fast_edge) {
+			if (code_bits == 2) alive_bits = tile_fast2_block<MODE, CPT, 1, false>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase, 0u, 0u, -1, sc, done_t, done_last);
+			else alive_bits = tile_fast2_block<MODE, CPT, 2, false>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase, 0u, 0u, -1, sc, done_t, done_last);
+			__syncthreads();
+		} else {
+			/* what lies outside the band of the block's first score reads as NEG_INF in every row (the reference's pads; stale or
+			 * trimmed cells otherwise) */
+			uint32_t outl = 0, outr = 0;
+#pragma unroll
+			for (int j = 0; j < CPT; ++j) {
+				if (left_edge && d0 + j < wflo_c) outl |= 1u << j;
+				if (right_edge && d0 + j > wfhi_c) outr |= 1u << j;
+			}
+			if (outl | outr) {
+				const uint32_t out = outl | outr;
+				for (int r = 0; r < R; ++r) {
+#pragma unroll
+					for (int j = 0; j < CPT; ++j)
+						if (out >> j & 1) asm volatile("st.shared.b32 [%0], %1;" :: "r"(sb + (uint32_t)r * rb + 4u * j), "r"(NEG_INF) : "memory");
+				}
+			}
+			if (tid < 4) sc[12 + tid] = 0;
+			if (!useful) outl = outr = 0; /* (halo cells are some other tile's, or nobody's) */
+			const int jfin = useful && dfin >= d0 && dfin < d0 + CPT ? dfin - d0 : -1;
+			if (code_bits == 2) alive_bits = tile_fast2_block<MODE, CPT, 1, true>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase, outl, outr, jfin, sc, done_t, done_last);
+			else alive_bits = tile_fast2_block<MODE, CPT, 2, true>(c, steptab, sv, d1 * rb, d2 * rb, d0, Tb, t_alive, tl, ql, useful, tbp, tb_pitch, stepbar, step_phase, outl, outr, jfin, sc, done_t, done_last);
+			__syncthreads();
+			/* the slices' bounds, score by score, for the planner's replay (:417-418): bit t - 1 of a mask = the band took a cell in step t */
+			const unsigned long long ml = (unsigned long long)(unsigned int)sc[12] | (unsigned long long)(unsigned int)sc[13] << 32;
+			const unsigned long long mr = (unsigned long long)(unsigned int)sc[14] | (unsigned long long)(unsigned int)sc[15] << 32;
+			if (tid < Tb) {
+				const unsigned long long before = (1ull << tid) - 1;
+				if (left_edge) ctl->lo_log[tid] = max(wflo_c - __popcll(ml & before) - 1, -tl);
+				if (right_edge) ctl->hi_log[tid] = min(wfhi_c + __popcll(mr & before) + 1, ql);
+			}
+			wflo_c -= __popcll(ml), wfhi_c += __popcll(mr);
+			if (done_t != 0x7fffffff && __ldcg(&ctl->done_t) == 0x7fffffff) { ctl->done_t = done_t; ctl->done_last = done_last; } /* (one thread holds the terminal diagonal) */
+			__syncthreads(); /* sc[12..] is the caller's again */
+		}
 		stepped = true;
 	}
 	if constexpr (CPT == 4) {
@@ -1645,7 +1722,7 @@ __global__ void wfa_tile_segstart_kernel(const TParams P, int j_first)
 		for (int x = blockIdx.y * blockDim.x + threadIdx.x; x < n4; x += gridDim.y * blockDim.x) d4[x] = s4[x];
 	}
 	if (blockIdx.y == 0 && threadIdx.x == 0) {
-		c->s = d.s, c->wflo = d.wflo, c->wfhi = d.wfhi, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = d.n_iter;
+		c->s = d.s, c->wflo = d.wflo, c->wfhi = d.wfhi, c->cur = 0, c->last = 0, c->sid = 0, c->copied = 0, c->n_iter = d.n_iter, c->shrink_s = d.s, c->nat_ok = 0;
 		c->Tb = 0, c->n_tiles = 0, c->done_t = 0x7fffffff, c->done_last = 0, c->snap_off = -1, c->tiles_done = 0;
 		c->status = TS_RUN;
 		atomicAdd(P.n_running, 1);
