@@ -605,9 +605,81 @@ __device__ bool trace_checkpoints(const Job &J, const Pen &pen, int n_snap, int 
  * lines are prefetched 256 bases ahead (150 kb pair, 10 924 CIGAR operations: 7.5 -> 6.8 ms). */
 #define TB_ROWWIN 2048 /* entries of the row table a traceback warp keeps in shared memory */
 
+/* The bytes a walk can reach next lie in a cone below its position: at most max-penalty rows down and one diagonal sideways per
+ * step.  TbCone keeps TBC_ROWS rows x TBC_COLS diagonals around the position in shared memory, filled by the whole warp with
+ * aligned word loads that are all in flight together: one DRAM latency per ~25 steps of the walk instead of one per step. */
+#define TBC_ROWS 128
+#define TBC_COLS 32
+#define TBC_WORDS (TBC_COLS / 4 + 2) /* per row: the columns plus the slack of rounding the row's address down to a word */
+struct TbCone {
+	uint32_t w[TBC_ROWS * TBC_WORDS];
+	long long rt[TBC_ROWS]; /* row-table entries of the cached rows, rt[r] of row top - r */
+};
+struct TbConePos { int top, lo; long long c0; }; /* rows [lo, top], columns [c0, c0 + TBC_COLS) (column = diagonal + doff) */
+
+/* the match runs walk both sequences backwards, 32 bytes at a time: a window of each in shared memory, refilled every ~1000 bases */
+#define TBS_WIN 1024
+struct TbSeqWin { uint8_t q[TBS_WIN], t[TBS_WIN]; };
+__device__ __forceinline__ int tbseq_fill(uint8_t *dst, const uint8_t *src, int pos) /* bytes [base, pos] of src (16-byte aligned); returns base */
+{
+	const int lane = threadIdx.x & 31, b = max(0, pos - (TBS_WIN - 16)) & ~15;
+	uint4 v[TBS_WIN / 512];
+	__syncwarp();
+#pragma unroll
+	for (int u = 0; u < TBS_WIN / 512; ++u) {
+		const int off = 16 * (lane + 32 * u);
+		v[u] = b + off <= pos ? __ldg(reinterpret_cast<const uint4*>(src + b + off)) : make_uint4(0, 0, 0, 0);
+	}
+#pragma unroll
+	for (int u = 0; u < TBS_WIN / 512; ++u) *reinterpret_cast<uint4*>(dst + 16 * (lane + 32 * u)) = v[u];
+	__syncwarp();
+	return b;
+}
+
+template<class RowTab>
+__device__ __forceinline__ void tbcone_fill(TbCone *cn, TbConePos &cp, const uint8_t *arena, long long arena_cap, const RowTab &rowtab, int row, long long col)
+{
+	const int lane = threadIdx.x & 31;
+	cp.top = row, cp.lo = max(1, row - TBC_ROWS + 1), cp.c0 = col - TBC_COLS / 2;
+	const int nrows = cp.top - cp.lo + 1;
+	__syncwarp();
+	{ /* (loads first, stores after: every load of the warp is in flight before the first is waited for) */
+		long long v[TBC_ROWS / 32];
+#pragma unroll
+		for (int u = 0; u < TBC_ROWS / 32; ++u) v[u] = lane + 32 * u < nrows ? rowtab(row - (lane + 32 * u)) : 0;
+#pragma unroll
+		for (int u = 0; u < TBC_ROWS / 32; ++u) cn->rt[lane + 32 * u] = v[u];
+	}
+	__syncwarp();
+	const long long last_word = (arena_cap - 4) & ~3LL;
+	constexpr int PER = TBC_ROWS * TBC_WORDS / 32;
+	uint32_t v[PER];
+#pragma unroll
+	for (int u = 0; u < PER; ++u) {
+		const int idx = lane + 32 * u, r = idx / TBC_WORDS, q = idx - r * TBC_WORDS;
+		long long a = ((cn->rt[r] + cp.c0) & ~3LL) + 4 * q;
+		a = a < 0 ? 0 : a > last_word ? last_word : a; /* (a word off the arena is never one the walk uses) */
+		v[u] = r < nrows ? __ldcg(reinterpret_cast<const uint32_t*>(arena + a)) : 0u;
+	}
+#pragma unroll
+	for (int u = 0; u < PER; ++u) cn->w[lane + 32 * u] = v[u];
+	__syncwarp();
+}
+__device__ __forceinline__ bool tbcone_has(const TbConePos &cp, int row, long long col)
+{
+	return row <= cp.top && row >= cp.lo && col >= cp.c0 && col < cp.c0 + TBC_COLS;
+}
+__device__ __forceinline__ int tbcone_get(const TbCone *cn, const TbConePos &cp, int row, long long col)
+{
+	const int r = cp.top - row;
+	const long long rt = cn->rt[r];
+	const int b = (int)((rt + col) - ((rt + cp.c0) & ~3LL));
+	return reinterpret_cast<const uint8_t*>(cn->w)[r * (TBC_WORDS * 4) + b];
+}
+
 /* rtw: TB_ROWWIN entries of shared memory for a sliding window of the row table (the walk needs rowtab[row - penalty] before every
  * traceback byte: from shared memory that is one dependent global load less per step), or null */
-__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state, long long *rtw = 0)
+__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state, long long *rtw = 0, TbCone *cone = 0, TbSeqWin *sw = 0)
 {
 	const int lane = threadIdx.x & 31, doff = J.doff;
 	int i = J.ql - 1, k = J.tl - 1, row = s_final, n_out = 0, cur_op = -1;
@@ -630,7 +702,17 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 		} \
 	} while (0)
 	RT_REFILL();
-	int x = row >= 1 ? (int)__ldcg(J.arena + RT(row) + (i - k + doff)) : 0; /* the byte of (row, i - k): a match run keeps the diagonal */
+	TbConePos cp;
+	cp.top = -1, cp.lo = 0, cp.c0 = 0;
+	int qwb = 0x7fffffff, twb = 0x7fffffff; /* first byte of each sequence window */
+	auto rowtab_at = [&](int r_) -> long long { return RT(r_); };
+#define CONE_REFILL() do { \
+		const long long col_ = (long long)(i - k + doff); \
+		if (cone && row >= 1 && (row > cp.top || (row - maxpen < cp.lo && cp.lo > 1) || col_ - 1 < cp.c0 || col_ + 1 >= cp.c0 + TBC_COLS)) \
+			tbcone_fill(cone, cp, J.arena, J.arena_cap, rowtab_at, row, col_); \
+	} while (0)
+	CONE_REFILL();
+	int x = row < 1 ? 0 : cone ? tbcone_get(cone, cp, row, i - k + doff) : (int)__ldcg(J.arena + RT(row) + (i - k + doff)); /* the byte of (row, i - k): a match run keeps the diagonal */
 #define CIG_PUSH(op_, len_) do { \
 		if ((op_) == cur_op) cur_len += (len_); \
 		else { if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; } cur_op = (op_), cur_len = (len_); } \
@@ -639,21 +721,35 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 #define SUCCESSORS(dst_) do { \
 		(dst_) = 0; \
 		if (lane < 9 && row - cpen >= 1) { \
-			long long off_ = RT(row - cpen) + (i - k + cdd + doff); \
-			off_ = off_ < 0 ? 0 : off_ >= J.arena_cap ? J.arena_cap - 1 : off_; \
-			(dst_) = __ldcg(J.arena + off_); \
+			if (cone && tbcone_has(cp, row - cpen, (long long)(i - k + cdd + doff))) (dst_) = tbcone_get(cone, cp, row - cpen, (long long)(i - k + cdd + doff)); \
+			else { \
+				long long off_ = RT(row - cpen) + (i - k + cdd + doff); \
+				off_ = off_ < 0 ? 0 : off_ >= J.arena_cap ? J.arena_cap - 1 : off_; \
+				(dst_) = __ldcg(J.arena + off_); \
+			} \
 		} \
 	} while (0)
 	int xs;
 	SUCCESSORS(xs);
+#ifdef MWF_PHASE_PROF
+	long long tw_run = 0, tw_rest = 0, tw_fill = 0, tw_n = 0, tw_chunks = 0, tw_t = clock64();
+#define TW(acc) do { const long long n_ = clock64(); acc += n_ - tw_t; tw_t = n_; } while (0)
+#else
+#define TW(acc) do {} while (0)
+#endif
 	while (i >= 0 && k >= 0) {
-		if (lane == 9 && i >= 256) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.Q8 + (i - 256))); /* the match runs walk both */
-		if (lane == 10 && k >= 256) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.T8 + (k - 256))); /* sequences backwards */
+		if (!sw && lane == 9 && i >= 256) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.Q8 + (i - 256))); /* the match runs walk both */
+		if (!sw && lane == 10 && k >= 256) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.T8 + (k - 256))); /* sequences backwards */
 		if (last == 0) { /* greedy backward matches, :335-341 */
 			int run = 0;
 			for (;;) {
 				const int ii = i - lane, kk = k - lane;
-				const bool same = ii >= 0 && kk >= 0 && J.Q8[ii] == J.T8[kk];
+				bool same;
+				if (sw) {
+					if (qwb > max(0, i - 31)) qwb = tbseq_fill(sw->q, J.Q8, i);
+					if (twb > max(0, k - 31)) twb = tbseq_fill(sw->t, J.T8, k);
+					same = ii >= 0 && kk >= 0 && sw->q[ii - qwb] == sw->t[kk - twb];
+				} else same = ii >= 0 && kk >= 0 && __ldg(J.Q8 + ii) == __ldg(J.T8 + kk);
 				const unsigned m = __ballot_sync(0xffffffffu, !same);
 				if (m) { const int c = __ffs(m) - 1; run += c, i -= c, k -= c; break; }
 				run += 32, i -= 32, k -= 32;
@@ -661,6 +757,7 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 			if (run > 0) CIG_PUSH(7, (uint32_t)run);
 			if (i < 0 || k < 0) break;
 		}
+		TW(tw_run);
 		const int state = last == 0 ? (x & 7) : last;
 		const int ext = state > 0 ? (x >> (state + 2)) & 1 : 0;
 		int csel = 0, xs_next;
@@ -673,10 +770,22 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 		last = (state > 0 && ext) ? state : 0;
 		x = __shfl_sync(0xffffffffu, xs, csel);
 		RT_REFILL();
+		TW(tw_rest);
+		CONE_REFILL();
+		TW(tw_fill);
 		SUCCESSORS(xs_next); /* (issuing these before the shuffle was slower on the box: 8.1 ms against 6.8 ms on the 150 kb pair) */
 		xs = xs_next;
+		TW(tw_rest);
+#ifdef MWF_PHASE_PROF
+		++tw_n;
+#endif
 	}
+#ifdef MWF_PHASE_PROF
+	if (lane == 0) printf("[walk] %lld steps: match runs %lld, cone fills %lld, rest %lld cycles per step\n", tw_n, tw_run / max(tw_n, 1LL), tw_fill / max(tw_n, 1LL), tw_rest / max(tw_n, 1LL));
+#endif
+#undef TW
 #undef SUCCESSORS
+#undef CONE_REFILL
 #undef RT_REFILL
 #undef RT
 	end_state[0] = row, end_state[1] = i, end_state[2] = k; /* :367 */

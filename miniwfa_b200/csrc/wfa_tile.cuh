@@ -1632,7 +1632,7 @@ __global__ void wfa_tile_checkpoint_kernel(const TParams P)
 		if (last == 0) { /* greedy backward matches (:335-341): no score, no diagonal change */
 			for (;;) {
 				const int ii = i - lane, kk = k - lane;
-				const bool same = ii >= 0 && kk >= 0 && Q8[ii] == T8[kk];
+				const bool same = ii >= 0 && kk >= 0 && __ldg(Q8 + ii) == __ldg(T8 + kk);
 				const unsigned m = __ballot_sync(0xffffffffu, !same);
 				if (m) { const int cnt = __ffs(m) - 1; i -= cnt, k -= cnt; break; }
 				i -= 32, k -= 32;
@@ -1668,7 +1668,9 @@ __global__ void wfa_tile_traceback_kernel(const TParams P)
 	J.rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
 	int end_state[3];
 	__shared__ long long rtw[TB_ROWWIN];
-	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state, rtw);
+	__shared__ TbCone cone;
+	__shared__ __align__(16) TbSeqWin sw;
+	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state, rtw, &cone, &sw);
 	if (threadIdx.x == 0) {
 		P.outs[pi].end_s = end_state[0], P.outs[pi].end_i = end_state[1], P.outs[pi].end_k = end_state[2];
 		P.outs[pi].n_cigar = n_cigar;
@@ -1750,6 +1752,12 @@ __global__ void wfa_tile_trace_seg_kernel(const TParams P, int j, int vslot0)
 	int i = t.i, k = t.k, row = t.row, last = t.last, cur_op = t.cur_op, n_out = t.n_out;
 	uint32_t cur_len = t.cur_len;
 	uint32_t *wp = P.cigar + pd.cigar_off + pd.cigar_cap - n_out;
+	__shared__ TbCone cone; /* the traceback bytes around the walk (wfa_engine.cu) */
+	__shared__ __align__(16) TbSeqWin sw; /* and the sequences under the match runs */
+	int qwb = 0x7fffffff, twb = 0x7fffffff;
+	TbConePos cp;
+	cp.top = -1, cp.lo = 0, cp.c0 = 0;
+	auto rowtab_at = [&](int r_) -> long long { return rowtab[r_]; };
 #define CIG_PUSH(op_, len_) do { \
 		if ((op_) == cur_op) cur_len += (len_); \
 		else { if (cur_op >= 0) { --wp; if (lane == 0) *wp = cur_len << 4 | (uint32_t)cur_op; ++n_out; } cur_op = (op_), cur_len = (len_); } \
@@ -1759,7 +1767,9 @@ __global__ void wfa_tile_trace_seg_kernel(const TParams P, int j, int vslot0)
 			int run = 0;
 			for (;;) {
 				const int ii = i - lane, kk = k - lane;
-				const bool same = ii >= 0 && kk >= 0 && Q8[ii] == T8[kk];
+				if (qwb > max(0, i - 31)) qwb = tbseq_fill(sw.q, Q8, i);
+				if (twb > max(0, k - 31)) twb = tbseq_fill(sw.t, T8, k);
+				const bool same = ii >= 0 && kk >= 0 && sw.q[ii - qwb] == sw.t[kk - twb];
 				const unsigned m = __ballot_sync(0xffffffffu, !same);
 				if (m) { const int cnt = __ffs(m) - 1; run += cnt, i -= cnt, k -= cnt; break; }
 				run += 32, i -= 32, k -= 32;
@@ -1768,7 +1778,9 @@ __global__ void wfa_tile_trace_seg_kernel(const TParams P, int j, int vslot0)
 			if (i < 0 || k < 0) break;
 		}
 		if (row <= s_lo && j > 0) break; /* this row's bytes belong to an earlier segment */
-		const int x = __ldcg(P.arena + rowtab[row] + (i - k + doff));
+		const long long col = (long long)(i - k + doff);
+		if (!tbcone_has(cp, row, col)) tbcone_fill(&cone, cp, P.arena, P.arena_cap, rowtab_at, row, col);
+		const int x = tbcone_get(&cone, cp, row, col);
 		const int state = last == 0 ? (x & 7) : last;
 		const int ext = state > 0 ? (x >> (state + 2)) & 1 : 0;
 		if (state == 0) { CIG_PUSH(8, 1u); --i, --k; row -= pen.x; }
@@ -1823,7 +1835,7 @@ __global__ void wfa_tile_ckpt_seg_kernel(const TParams P, int j)
 		if (last == 0) {
 			for (;;) {
 				const int ii = i - lane, kk = k - lane;
-				const bool same = ii >= 0 && kk >= 0 && Q8[ii] == T8[kk];
+				const bool same = ii >= 0 && kk >= 0 && __ldg(Q8 + ii) == __ldg(T8 + kk);
 				const unsigned m = __ballot_sync(0xffffffffu, !same);
 				if (m) { const int cnt = __ffs(m) - 1; i -= cnt, k -= cnt; break; }
 				i -= 32, k -= 32;
