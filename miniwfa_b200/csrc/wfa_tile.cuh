@@ -53,6 +53,8 @@ struct TileCtl { /* per pair, lives in HBM for the whole run */
 	int lo_log[TILE_TMAX], hi_log[TILE_TMAX];
 };
 
+#define TILE_CTL_HEAD 28 /* ints before lo_log */
+
 struct TileCounters { unsigned int n_items, next; };
 
 /* persistent scheduling (wfa_tile_persist_kernel): one queue of work items per pass, fed by the planner that runs inside the
@@ -265,21 +267,37 @@ template<bool PERSIST>
 __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *retire)
 {
 	__shared__ int sh[4];
-	__shared__ int widths[TILE_TMAX];
 	__shared__ long long sh_row[2];
 	__shared__ int sh_emit[4]; /* items base, n_tiles, first score of the rows, number of rows */
+	static_assert(offsetof(TileCtl, lo_log) == 4 * TILE_CTL_HEAD, "TileCtl: the scalar fields come first");
+	/* scratch: inside the persistent kernel the CTA's tile rows are idle while it plans (the kernel's static shared memory decides
+	 * whether a fourth CTA fits an SM); the one-CTA-per-pair plan kernel has its own */
+	__shared__ __align__(8) int scratch_s[PERSIST ? 2 : TILE_TMAX + TILE_CTL_HEAD + 4];
+	extern __shared__ __align__(128) int32_t smem_tile[];
+	int *const head = PERSIST ? reinterpret_cast<int*>(smem_tile) : scratch_s;
+	int *const widths = head + TILE_CTL_HEAD + 4;
 	const int pslot = pair_slot(P, slot), pi = P.order[P.pair0 + pslot];
 	TileCtl *c = P.ctl + slot;
-#define CL(f) __ldcg(&c->f) /* TileCtl is written by other SMs inside the persistent kernel: read it from L2 */
-	__syncthreads(); /* (the shared words above may still be read by the previous call) */
+	/* TileCtl is written by other SMs inside the persistent kernel: read from L2, and all of it at once -- its scalar fields, the
+	 * per-score bounds the tiles logged and the stop request come in with ONE round trip (a block of a single large pair waits for
+	 * this function; field by field it was ten dependent round trips, ~7 us).  CL(f) reads the copy; the few fields thread 0 changes
+	 * and reads again go through CSET. */
+	TileCtl *hw = reinterpret_cast<TileCtl*>(head);
+#define CL(f) (const_cast<const TileCtl*>(hw)->f)
+#define CSET(f, v) do { c->f = (v); hw->f = (v); } while (0)
+	__syncthreads(); /* (the shared words may still be read by the previous call) */
+	for (int t = threadIdx.x; t <= TILE_TMAX + TILE_CTL_HEAD; t += blockDim.x) { /* (CTAs of 64 threads and more) */
+		if (t < TILE_TMAX) widths[t] = __ldcg(&c->hi_log[t]) - __ldcg(&c->lo_log[t]) + 1;
+		else if (t < TILE_TMAX + TILE_CTL_HEAD) head[t - TILE_TMAX] = __ldcg(reinterpret_cast<const int*>(c) + (t - TILE_TMAX));
+		else head[TILE_CTL_HEAD] = PERSIST ? *(volatile int*)&P.pq->stop_req : 0;
+	}
+	__syncthreads();
 	if (CL(status) != TS_RUN) return;
 	const PairDesc pd = P.pairs[pi];
 	const int tl = pd.tl, ql = pd.ql, n = P.pen.nring, doff = tile_doff(P, tl);
 	int status = TS_RUN, s = CL(s), wflo = CL(wflo), wfhi = CL(wfhi);
 	const int Tb_done = CL(Tb);
 	if (Tb_done > 0) { /* replay, in the order of miniwfa.c:419-426 */
-		if (threadIdx.x < Tb_done) widths[threadIdx.x] = CL(hi_log[threadIdx.x]) - CL(lo_log[threadIdx.x]) + 1; /* all loads in flight at once */
-		__syncthreads();
 		if (threadIdx.x == 0) {
 			long long n_iter = CL(n_iter);
 			const int Tb = Tb_done, s0 = s, done_t = CL(done_t);
@@ -290,7 +308,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 				if ((P.max_iter > 0 && n_iter > P.max_iter) || (P.max_s > 0 && s > P.max_s)) { status = TS_STOPPED; break; }
 				if (done_t == t) { status = TS_DONE; last = CL(done_last); break; }
 			}
-			c->n_iter = n_iter, c->s = s, c->last = last;
+			CSET(n_iter, n_iter); c->s = s, c->last = last; /* (the other threads may still be reading s from the copy) */
 			c->wflo = CL(fin_lo), c->wfhi = CL(fin_hi), c->cur = CL(cur) ^ 1;
 			sh[0] = status, sh[1] = s;
 		}
@@ -319,7 +337,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 			const int nl = sh[2], nh = sh[3];
 			if (nl > wfhi || nh < nl) status = TS_SHRINK; /* the reference asserts (:157, :169) */
 			else {
-				if (threadIdx.x == 0 && (nl != wflo || nh != wfhi)) c->shrink_s = s;
+				if (threadIdx.x == 0 && (nl != wflo || nh != wfhi)) CSET(shrink_s, s);
 				wflo = nl, wfhi = nh;
 			}
 		}
@@ -330,7 +348,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 	bool park = false;
 	if (status == TS_RUN && s > P.s_limit) status = TS_SHRINK; /* cannot happen: the all-gap alignment costs less */
 	if (status == TS_RUN && P.s_stop && s >= P.s_stop[slot]) status = TS_SEGEND; /* end of a traceback segment */
-	if (PERSIST && status == TS_RUN && *(volatile int*)&P.pq->stop_req) { /* the other tile geometry takes over: the next launch cuts the block */
+	if (PERSIST && status == TS_RUN && head[TILE_CTL_HEAD]) { /* the other tile geometry takes over: the next launch cuts the block */
 		park = true;
 		c->wflo = wflo, c->wfhi = wfhi;
 		atomicSub(&P.pq->total_tiles, CL(n_tiles));
@@ -345,7 +363,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 			                                                  that follow store only their own columns, but still read the wide slices */
 			else {
 				wflo = wfhi = seg[2 * sid + 1];
-				++sid, c->copied = 0, c->shrink_s = s;
+				++sid, c->copied = 0; CSET(shrink_s, s);
 			}
 		}
 		Tb = min(P.T, ((s | 0xff) + 1) - s);
@@ -407,7 +425,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 		if (PERSIST) atomicSub(&P.pq->total_tiles, CL(n_tiles));
 		if (status != TS_SEGEND) { /* (a segment's end leaves the result record to the pass that reaches the end) */
 			PairOut o;
-			o.s = status == TS_DONE ? CL(s) : -1;
+			o.s = status == TS_DONE ? s : -1;
 			o.n_cigar = 0, o.n_iter = CL(n_iter), o.cigar_pos = pd.cigar_off + pd.cigar_cap;
 			o.status = status == TS_DONE ? ST_OK : status == TS_STOPPED ? ST_STOPPED : status == TS_ARENA ? ST_ARENA : ST_SHRINK;
 			o.pad_ = 0;
@@ -440,6 +458,7 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 		P.rowtab[(size_t)pslot * P.rowtab_stride + sh_emit[2] + 1 + threadIdx.x] = sh_row[0] + (long long)threadIdx.x * sh_row[1];
 }
 #undef CL
+#undef CSET
 
 __global__ void __launch_bounds__(128) wfa_plan_kernel(const __grid_constant__ TParams P, int it)
 {
