@@ -407,10 +407,14 @@ __device__ __noinline__ void plan_pair(const TParams &P, int slot, int it, int *
 			c->done_t = 0x7fffffff, c->done_last = 0, c->tiles_done = 0;
 			c->nat_ok = s - CL(shrink_s) >= n;
 			if (PERSIST) {
-				sh_emit[0] = (int)atomicAdd(&P.pq->tail, (unsigned int)n_tiles), sh_emit[1] = n_tiles;
-				const int tot = atomicAdd(&P.pq->total_tiles, n_tiles - old_tiles) + n_tiles - old_tiles;
-				const int n_cut = P.n_geom > 1 ? atomicAdd(&P.pq->n_cut, 1) + 1 : 0;
-				if (P.n_geom > 1 && n_cut >= *(volatile int*)&P.pq->n_start && ((P.geom_id == 0 && tot >= P.many) || (P.geom_id == 1 && tot < P.many / 2)) && !*(volatile int*)&P.pq->stop_req) {
+				/* (issued back to back, used afterwards: each is a round trip to L2 on the critical path of a single pair's block) */
+				const unsigned int base_t = atomicAdd(&P.pq->tail, (unsigned int)n_tiles);
+				const int tot0 = atomicAdd(&P.pq->total_tiles, n_tiles - old_tiles);
+				int n_cut = 0, n_start = 0;
+				if (P.n_geom > 1) { n_cut = atomicAdd(&P.pq->n_cut, 1) + 1; n_start = *(volatile int*)&P.pq->n_start; }
+				sh_emit[0] = (int)base_t, sh_emit[1] = n_tiles;
+				const int tot = tot0 + n_tiles - old_tiles;
+				if (P.n_geom > 1 && n_cut >= n_start && ((P.geom_id == 0 && tot >= P.many) || (P.geom_id == 1 && tot < P.many / 2)) && !head[TILE_CTL_HEAD]) { /* (a request raised since the copy was taken is raised again, to the same geometry) */
 					P.pq->switch_to = P.geom_id ^ 1;
 					__threadfence();
 					*(volatile int*)&P.pq->stop_req = 1;
