@@ -7,6 +7,7 @@ print("| kernel | instructions | " + " | ".join(c.strip() for c in cols) + " |")
 print("|---|---:|" + "---:|" * len(cols))
 for blk in txt.split("Function : ")[1:]:
     name = blk.split("\n", 1)[0].strip()
+    if name.startswith("_ZN3cub"): continue  # (CUB radix sort of the k-mer front end: library code)
     lines = [l for l in blk.split("\n") if re.search(r"/\*[0-9a-f]{4,5}\*/", l)]
     cnt = []
     for c in cols:
