@@ -472,6 +472,31 @@ def test_tile_geometry_variants(monkeypatch):
                 assert b.fetch() == want[i], (cpt, nt, T, wave, kw)
 
 
+def test_edge_tiles_on_the_register_resident_step(monkeypatch):
+    """Tiles at the band's edges grow the band from the recurrence itself (MWF_B200_TILE_FASTEDGE, default on) or with round 1's
+    per-score masks: same bits as the CPU checker both ways -- on pairs of unequal length (the band reaches a corner of the matrix
+    and trims take diagonals away), with stops, with traceback, in low-memory mode, on two- and four-bit codes."""
+    mw.set_kernel(mw.KERNEL_TILE)
+    rng = random.Random(11)
+    pairs = []
+    for i, (n, m, p) in enumerate(((12000, 7000, 0.03), (5000, 9000, 0.05), (8000, 8000, 0.1), (3000, 2900, 0.02), (700, 6000, 0.05), (6000, 6100, 0.3))):
+        t = bytes(rng.choice(b"ACGT" if i % 2 else b"ACGTN") for _ in range(n))
+        q = mutate(rng, t, p)
+        q = q[:m] if len(q) >= m else q + bytes(rng.choice(b"ACGT") for _ in range(m - len(q)))
+        pairs.append((t, q))
+    for kw in ({}, {"flag": mw.F_CIGAR}, {"max_iter": 2000000}, {"max_s": 3000}, {"flag": mw.F_CIGAR, "step": 700}):
+        want = [orc.checker_exact(orc.make_opt(**kw), t, q) for t, q in pairs]
+        for fe in ("1", "0"):
+            monkeypatch.setenv("MWF_B200_TILE_FASTEDGE", fe)
+            for T in ("32", "64"):
+                monkeypatch.setenv("MWF_B200_TILE_T", T)
+                with mw.Batch(mw.opt_init(**kw), pairs) as b:
+                    assert b.kernel_used == mw.KERNEL_TILE
+                    b.upload()
+                    b.run()
+                    assert b.fetch() == want, (kw, fe, T)
+
+
 def test_lowmem_when_the_highmem_pass_does_not_fit(monkeypatch):
     """Low-memory requests run on the tile engine through an unbanded high-memory pass; when its s^2 traceback bytes do not
     fit the arena the checkpoints come from the segmented walk (snapshots + recompute), or, on request, from the reference's
