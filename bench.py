@@ -573,6 +573,17 @@ def main():
                       "api": "mwf_wfa_exact() with host buffers (create, H2D, kernels, traceback, D2H, CIGAR into the caller's km)"},
               "roofline_frac": r1[2] * BYTES_PER_CELL_TB / (kms * 1e-3) / 1e9 / peak,
               "note": "one pair = one dependency chain of s scores: latency-bound, not HBM-bound"}
+        # latency of one tiny call (there is no CPU path, so a t3-sized pair pays create / upload / run / fetch).
+        # Taken right after the GPU-bound calls above: after seconds of an idle GPU (the CPU leg below) the same call was measured
+        # at 0.8-1.3 ms until the device had been busy again (tools/tiny_latency.py).
+        tt = []
+        for _ in range(50):
+            t0 = time.perf_counter()
+            rt = mw.wfa_exact(o2, b"ACGTACGTACGTTTGACA" * 4, b"ACGTACGAACGTTTGACA" * 4)
+            tt.append(time.perf_counter() - t0)
+        tt.sort()
+        line["tiny_pair_latency"] = {"workload": "mwf_wfa_exact() on a 72 bp pair with CIGAR, host buffers, 50 calls after a busy GPU", "s": rt[0],
+                                     "median_us": statistics.median(tt) * 1e6, "min_us": tt[0] * 1e6, "p90_us": tt[44] * 1e6}
         if c2 is not None:
             e = c2["expect"]
             assert (r1[0], r1[1], r1[2], sha1_words(r1[3])) == (e["s"], e["n_cigar"], e["n_iter"], e["cigar_sha1"]), "config 2 differs from the reference"
@@ -584,14 +595,6 @@ def main():
                                   "sample": "the whole pair, one host thread; s, n_iter and all CIGAR words equal to the GPU's",
                                   "build": cpu_build_note()}
             sp["parity"] = "reference: every CIGAR word, s, n_iter equal to the %s run beside it%s" % (kind, " and to golden_large.json:config2-c" if c2 else "")
-        # latency of one tiny call (there is no CPU path, so a t3-sized pair pays create / upload / run / fetch)
-        tt = []
-        for _ in range(20):
-            t0 = time.perf_counter()
-            rt = mw.wfa_exact(o2, b"ACGTACGTACGTTTGACA" * 4, b"ACGTACGAACGTTTGACA" * 4)
-            tt.append(time.perf_counter() - t0)
-        line["tiny_pair_latency"] = {"workload": "mwf_wfa_exact() on a 72 bp pair with CIGAR, host buffers", "s": rt[0],
-                                     "median_us": statistics.median(tt) * 1e6, "min_us": min(tt) * 1e6}
         line["single_pair"] = sp
 
     # ---- 5 Mb pairs (config 4 and config 5 surrogates, one pair each), rank 0 --------------------------------------------
