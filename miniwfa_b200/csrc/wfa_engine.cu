@@ -609,7 +609,7 @@ __device__ bool trace_checkpoints(const Job &J, const Pen &pen, int n_snap, int 
  * step.  TbCone keeps TBC_ROWS rows x TBC_COLS diagonals around the position in shared memory, filled by the whole warp with
  * aligned word loads that are all in flight together: one DRAM latency per ~25 steps of the walk instead of one per step. */
 #define TBC_ROWS 128
-#define TBC_COLS 32
+#define TBC_COLS 24 /* (+ 2 words of slack = 8 words per row: a warp instruction covers four rows, index arithmetic by shifts) */
 #define TBC_WORDS (TBC_COLS / 4 + 2) /* per row: the columns plus the slack of rounding the row's address down to a word */
 struct TbCone {
 	uint32_t w[TBC_ROWS * TBC_WORDS];
@@ -665,6 +665,29 @@ __device__ __forceinline__ void tbcone_fill(TbCone *cn, TbConePos &cp, const uin
 	for (int u = 0; u < PER; ++u) cn->w[lane + 32 * u] = v[u];
 	__syncwarp();
 }
+/* the same fill with cp.async: nothing is waited for and no register holds the data; the walk goes on in the cone it is in and
+ * switches to this one, long landed, when it leaves the other (cp.async.wait_group 0 + __syncwarp before the first read) */
+template<class RowTab>
+__device__ __forceinline__ void tbcone_prefetch(TbCone *cn, TbConePos &cp, const uint8_t *arena, long long arena_cap, const RowTab &rowtab, int row, long long col)
+{
+	const int lane = threadIdx.x & 31;
+	cp.top = row, cp.lo = max(1, row - TBC_ROWS + 1), cp.c0 = col - TBC_COLS / 2;
+	const int nrows = cp.top - cp.lo + 1;
+	__syncwarp();
+#pragma unroll
+	for (int u = 0; u < TBC_ROWS / 32; ++u) cn->rt[lane + 32 * u] = lane + 32 * u < nrows ? rowtab(row - (lane + 32 * u)) : 0;
+	__syncwarp();
+	const long long last_word = (arena_cap - 4) & ~3LL;
+	constexpr int PER = TBC_ROWS * TBC_WORDS / 32;
+#pragma unroll 8
+	for (int u = 0; u < PER; ++u) {
+		const int idx = lane + 32 * u, r = idx / TBC_WORDS, q = idx - r * TBC_WORDS;
+		long long a = ((cn->rt[r] + cp.c0) & ~3LL) + 4 * q;
+		a = a < 0 ? 0 : a > last_word ? last_word : a;
+		if (r < nrows) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(&cn->w[idx])), "l"(arena + a) : "memory");
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ bool tbcone_has(const TbConePos &cp, int row, long long col)
 {
 	return row <= cp.top && row >= cp.lo && col >= cp.c0 && col < cp.c0 + TBC_COLS;
@@ -679,7 +702,7 @@ __device__ __forceinline__ int tbcone_get(const TbCone *cn, const TbConePos &cp,
 
 /* rtw: TB_ROWWIN entries of shared memory for a sliding window of the row table (the walk needs rowtab[row - penalty] before every
  * traceback byte: from shared memory that is one dependent global load less per step), or null */
-__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state, long long *rtw = 0, TbCone *cone = 0, TbSeqWin *sw = 0)
+__device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int last, uint32_t *cig_end, int *end_state, long long *rtw = 0, TbCone *cone = 0, TbSeqWin *sw = 0, TbCone *cone_b = 0)
 {
 	const int lane = threadIdx.x & 31, doff = J.doff;
 	int i = J.ql - 1, k = J.tl - 1, row = s_final, n_out = 0, cur_op = -1;
@@ -706,10 +729,23 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 	cp.top = -1, cp.lo = 0, cp.c0 = 0;
 	int qwb = 0x7fffffff, twb = 0x7fffffff; /* first byte of each sequence window */
 	auto rowtab_at = [&](int r_) -> long long { return RT(r_); };
+	TbConePos pp; /* the cone being fetched ahead into cone_b (or into cone, they swap), when `pending` */
+	bool pending = false;
+	pp.top = -1, pp.lo = 0, pp.c0 = 0;
+#define CONE_NEEDS(cp_, col_) (row > (cp_).top || (row - maxpen < (cp_).lo && (cp_).lo > 1) || (col_) - 1 < (cp_).c0 || (col_) + 1 >= (cp_).c0 + TBC_COLS)
 #define CONE_REFILL() do { \
 		const long long col_ = (long long)(i - k + doff); \
-		if (cone && row >= 1 && (row > cp.top || (row - maxpen < cp.lo && cp.lo > 1) || col_ - 1 < cp.c0 || col_ + 1 >= cp.c0 + TBC_COLS)) \
-			tbcone_fill(cone, cp, J.arena, J.arena_cap, rowtab_at, row, col_); \
+		if (cone && row >= 1 && CONE_NEEDS(cp, col_)) { \
+			bool have_ = false; \
+			if (pending) { /* the cone fetched ahead has landed long ago */ \
+				asm volatile("cp.async.wait_group 0;" ::: "memory"); \
+				__syncwarp(); \
+				pending = false; \
+				if (!CONE_NEEDS(pp, col_)) { TbCone *t_ = cone; cone = cone_b; cone_b = t_; cp = pp; have_ = true; } \
+			} \
+			if (!have_) tbcone_fill(cone, cp, J.arena, J.arena_cap, rowtab_at, row, col_); \
+		} else if (cone_b && !pending && row >= 1 && cp.lo > 1 && row - cp.lo < 56) /* 24 rows further down is where the walk will be when it leaves this cone */ \
+			tbcone_prefetch(cone_b, pp, J.arena, J.arena_cap, rowtab_at, max(1, row - 24), col_), pending = true; \
 	} while (0)
 	CONE_REFILL();
 	int x = row < 1 ? 0 : cone ? tbcone_get(cone, cp, row, i - k + doff) : (int)__ldcg(J.arena + RT(row) + (i - k + doff)); /* the byte of (row, i - k): a match run keeps the diagonal */
@@ -784,8 +820,10 @@ __device__ int traceback_warp(const Job &J, const Pen &pen, int s_final, int las
 	if (lane == 0) printf("[walk] %lld steps: match runs %lld, cone fills %lld, rest %lld cycles per step\n", tw_n, tw_run / max(tw_n, 1LL), tw_fill / max(tw_n, 1LL), tw_rest / max(tw_n, 1LL));
 #endif
 #undef TW
+	if (pending) asm volatile("cp.async.wait_group 0;" ::: "memory");
 #undef SUCCESSORS
 #undef CONE_REFILL
+#undef CONE_NEEDS
 #undef RT_REFILL
 #undef RT
 	end_state[0] = row, end_state[1] = i, end_state[2] = k; /* :367 */

@@ -1691,9 +1691,9 @@ __global__ void wfa_tile_traceback_kernel(const TParams P)
 	J.rowtab = P.rowtab + (size_t)slot * P.rowtab_stride;
 	int end_state[3];
 	__shared__ long long rtw[TB_ROWWIN];
-	__shared__ TbCone cone;
+	__shared__ TbCone cone[2];
 	__shared__ __align__(16) TbSeqWin sw;
-	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state, rtw, &cone, &sw);
+	const int n_cigar = traceback_warp(J, P.pen, c->s, c->last, P.cigar + pd.cigar_off + pd.cigar_cap, end_state, rtw, cone, &sw, cone + 1);
 	if (threadIdx.x == 0) {
 		P.outs[pi].end_s = end_state[0], P.outs[pi].end_i = end_state[1], P.outs[pi].end_k = end_state[2];
 		P.outs[pi].n_cigar = n_cigar;
